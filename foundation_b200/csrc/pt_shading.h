@@ -1,0 +1,233 @@
+// pt_shading.h — the per-vertex shading arithmetic of the wavefront path tracer (stages B1, B3, B4
+// of SURVEY.md §8a2): camera ray generation, the diffuse + GGX surface model, one-sample next-event
+// estimation on emissive triangles with power-heuristic MIS, Russian roulette.
+//
+// Same rule as pt_math.h: only + - * / sqrt fma and the polynomial sincos, so the CUDA kernels and the
+// CPU oracle produce bit-identical radiance for identical PCG streams (north_star asks RMSE <= 1e-3; the
+// tests additionally record how many pixels differ at all).  The reference contains no shading model of
+// its own (its fragment shader is a texture fetch, src/Renderer/Triangle.slang:34-37); the camera
+// conventions come from src/Renderer/Renderer.cpp:373-380.
+#pragma once
+#include "pt_layout.h"
+
+#define PT_FLAG_NO_MATERIAL_SORT 1u
+#define PT_FLAG_NO_NEE 2u
+#define PT_FLAG_NO_BSDF_EMISSION 4u
+
+struct PtShadeConsts {
+    const PtLight* lights;
+    uint32_t num_lights;
+    float light_area;      // total emissive area (world space)
+    float ray_eps;         // origin offset along the normal for secondary rays
+    uint32_t flags;
+    uint32_t max_bounces;
+    float bg[3];
+};
+
+// Everything a path carries between bounces (SoA on the device, a local struct in the oracle).
+struct PtPath {
+    pt_v3 o, d;        // current ray (d normalised)
+    pt_v3 beta;        // throughput
+    pt_v3 L;           // radiance gathered by this sample so far
+    pt_rng rng;
+    float pdf_prev;    // solid-angle pdf of the BSDF sample that produced the current ray (0 on the primary ray)
+    uint32_t pixel;
+    uint32_t bounce;   // index of the vertex the current ray will hit (0 = primary)
+};
+
+struct PtShadowRay {
+    pt_v3 o, d;        // d unnormalised: the light point is at t = 1
+    float tmax;
+    pt_v3 contrib;     // added to L if unoccluded
+    bool valid;
+};
+
+// ---- B1: ray generation ---------------------------------------------------------------------------
+PT_HD void pt_camera_ray(const PtCamera& cam, uint32_t px, uint32_t py, uint32_t width, uint32_t height, float jx, float jy,
+                         pt_v3* o, pt_v3* d) {
+    // NDC of the sample: x right, y DOWN (Vulkan clip space after the reference's proj[1][1] *= -1), top-left pixel 0,0
+    float nx = pt_fma(((float)px + jx), pt_div(2.0f, (float)width), -1.0f);
+    float ny = pt_fma(((float)py + jy), pt_div(2.0f, (float)height), -1.0f);
+    pt_v3 dir = pt_mk(pt_fma(ny, cam.dy[0], pt_fma(nx, cam.dx[0], cam.d0[0])), pt_fma(ny, cam.dy[1], pt_fma(nx, cam.dx[1], cam.d0[1])),
+                      pt_fma(ny, cam.dy[2], pt_fma(nx, cam.dx[2], cam.d0[2])));
+    *o = pt_mk(cam.eye[0], cam.eye[1], cam.eye[2]);
+    *d = pt_normalize(dir);
+}
+
+PT_HD void pt_path_init(PtPath* p, const PtCamera& cam, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t width, uint32_t height) {
+    p->rng = pt_rng_for(seed, pixel, sample);
+    float jx = pt_rng_f(&p->rng), jy = pt_rng_f(&p->rng);
+    pt_camera_ray(cam, pixel % width, pixel / width, width, height, jx, jy, &p->o, &p->d);
+    p->beta = pt_mk(1.0f, 1.0f, 1.0f);
+    p->L = pt_mk(0.0f, 0.0f, 0.0f);
+    p->pdf_prev = 0.0f;
+    p->pixel = pixel;
+    p->bounce = 0;
+}
+
+// ---- surface model ----------------------------------------------------------------------------------
+struct PtBsdf {
+    pt_v3 kd, f0;
+    float alpha, a2, p_spec;
+};
+PT_HD PtBsdf pt_bsdf_make(const PtMaterial& m) {
+    PtBsdf b;
+    float om = 1.0f - m.metallic;
+    b.kd = pt_mk(m.r * om, m.g * om, m.b * om);
+    b.f0 = pt_mk(pt_fma(m.r - 0.04f, m.metallic, 0.04f), pt_fma(m.g - 0.04f, m.metallic, 0.04f), pt_fma(m.b - 0.04f, m.metallic, 0.04f));
+    b.alpha = pt_max(m.roughness * m.roughness, 1e-3f);
+    b.a2 = b.alpha * b.alpha;
+    b.p_spec = pt_fma(0.5f, m.metallic, 0.5f);
+    return b;
+}
+PT_HD float pt_lambda(float a2, float cz) {  // Smith Lambda for GGX, cz = cos(theta) > 0
+    float c2 = cz * cz;
+    float t2 = pt_div(pt_max(1.0f - c2, 0.0f), c2);
+    return 0.5f * (pt_sqrt(pt_fma(a2, t2, 1.0f)) - 1.0f);
+}
+// f (without the cosine) and the mixture pdf, local frame (z = shading normal), wo.z > 0, wi.z > 0
+PT_HD void pt_bsdf_eval(const PtBsdf& b, pt_v3 wo, pt_v3 wi, pt_v3* f, float* pdf) {
+    float woz = pt_max(wo.z, 1e-6f), wiz = pt_max(wi.z, 1e-6f);
+    pt_v3 h = pt_normalize(pt_add(wo, wi));
+    float dh = pt_max(pt_dot(wo, h), 0.0f);
+    float k = pt_fma(h.z * h.z, b.a2 - 1.0f, 1.0f);
+    float D = pt_div(b.a2, PT_PI * k * k);
+    float lo = pt_lambda(b.a2, woz), li = pt_lambda(b.a2, wiz);
+    float G2 = pt_div(1.0f, 1.0f + lo + li);
+    float G1 = pt_div(1.0f, 1.0f + lo);
+    float m = 1.0f - dh, m2 = m * m, m5 = m2 * m2 * m;
+    pt_v3 F = pt_mk(pt_fma(1.0f - b.f0.x, m5, b.f0.x), pt_fma(1.0f - b.f0.y, m5, b.f0.y), pt_fma(1.0f - b.f0.z, m5, b.f0.z));
+    float sp = pt_div(D * G2, 4.0f * woz * wiz);
+    *f = pt_mk(pt_fma(b.kd.x * PT_INV_PI, 1.0f - F.x, F.x * sp), pt_fma(b.kd.y * PT_INV_PI, 1.0f - F.y, F.y * sp),
+               pt_fma(b.kd.z * PT_INV_PI, 1.0f - F.z, F.z * sp));
+    float pdf_s = pt_div(G1 * D, 4.0f * woz);
+    float pdf_d = wiz * PT_INV_PI;
+    *pdf = pt_fma(b.p_spec, pdf_s, (1.0f - b.p_spec) * pdf_d);
+}
+// Samples wi (local). Returns false when the sample falls below the horizon.
+PT_HD bool pt_bsdf_sample(const PtBsdf& b, pt_v3 wo, float ul, float u1, float u2, pt_v3* wi) {
+    float s, c;
+    pt_sincos2pi(u2, &s, &c);
+    float r = pt_sqrt(u1);
+    if (ul < b.p_spec) {
+        // GGX visible-normal sampling (Heitz 2018)
+        pt_v3 vh = pt_normalize(pt_mk(b.alpha * wo.x, b.alpha * wo.y, wo.z));
+        float lensq = pt_fma(vh.x, vh.x, vh.y * vh.y);
+        pt_v3 t1 = pt_mk(1.0f, 0.0f, 0.0f);
+        if (lensq > 0.0f) { float il = pt_div(1.0f, pt_sqrt(lensq)); t1 = pt_mk(-vh.y * il, vh.x * il, 0.0f); }
+        pt_v3 t2 = pt_cross(vh, t1);
+        float a = r * c, bb = r * s;
+        float sw = 0.5f * (1.0f + vh.z);
+        bb = pt_fma(1.0f - sw, pt_sqrt(pt_max(pt_fma(-a, a, 1.0f), 0.0f)), sw * bb);
+        float cz = pt_sqrt(pt_max(1.0f - pt_fma(a, a, bb * bb), 0.0f));
+        pt_v3 nh = pt_madd(pt_madd(pt_scale(t1, a), bb, t2), cz, vh);
+        pt_v3 h = pt_normalize(pt_mk(b.alpha * nh.x, b.alpha * nh.y, pt_max(nh.z, 0.0f)));
+        float dh = pt_dot(wo, h);
+        *wi = pt_sub(pt_scale(h, 2.0f * dh), wo);
+    } else {
+        *wi = pt_mk(r * c, r * s, pt_sqrt(pt_max(1.0f - u1, 0.0f)));
+    }
+    return wi->z > 0.0f;
+}
+
+// first light whose cumulative area fraction reaches u
+PT_HD uint32_t pt_pick_light(const PtLight* lights, uint32_t n, float u) {
+    uint32_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (lights[mid].cdf < u) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- B3 + B4: shade one path vertex -------------------------------------------------------------------
+// Inputs: the path (current ray), the hit distance, the hit triangle in WORLD space (v0, e1, e2) and its
+// material.  Effects: adds emission to path->L, optionally emits one shadow ray, samples the BSDF and
+// rewrites the path's ray.  Returns true while the path is alive.  Consumes exactly 7 random numbers.
+PT_HD bool pt_shade_vertex(PtPath* path, const PtShadeConsts& sc, float t, pt_v3 e1, pt_v3 e2, const PtMaterial& mat, PtShadowRay* sh) {
+    sh->valid = false;
+    pt_v3 ng = pt_normalize(pt_cross(e1, e2));
+    float dn = pt_dot(ng, path->d);
+    bool front = dn < 0.0f;
+    pt_v3 n = front ? ng : pt_neg(ng);
+    bool emissive = (mat.er > 0.0f) || (mat.eg > 0.0f) || (mat.eb > 0.0f);
+    if (emissive) {
+        if (front) {
+            float w = 1.0f;
+            if (path->bounce > 0) {
+                if (sc.flags & PT_FLAG_NO_BSDF_EMISSION) w = 0.0f;
+                else if (!(sc.flags & PT_FLAG_NO_NEE) && sc.num_lights > 0) {
+                    float pl = pt_div(t * t, -dn * sc.light_area);
+                    float pb2 = path->pdf_prev * path->pdf_prev;
+                    w = pt_div(pb2, pt_fma(pl, pl, pb2));
+                }
+            }
+            path->L = pt_mk(pt_fma(path->beta.x * mat.er, w, path->L.x), pt_fma(path->beta.y * mat.eg, w, path->L.y),
+                            pt_fma(path->beta.z * mat.eb, w, path->L.z));
+        }
+        return false;  // emitters do not scatter
+    }
+    if (path->bounce >= sc.max_bounces) return false;
+
+    pt_v3 p = pt_madd(path->o, t, path->d);
+    pt_v3 po = pt_madd(p, sc.ray_eps, n);
+    pt_v3 T, B;
+    pt_onb(n, &T, &B);
+    pt_v3 wo_w = pt_neg(path->d);
+    pt_v3 wo = pt_mk(pt_dot(wo_w, T), pt_dot(wo_w, B), pt_dot(wo_w, n));
+    PtBsdf bsdf = pt_bsdf_make(mat);
+
+    // B4: next-event estimation (always consumes 3 numbers so the stream layout is fixed)
+    float u0 = pt_rng_f(&path->rng), u1 = pt_rng_f(&path->rng), u2 = pt_rng_f(&path->rng);
+    if (!(sc.flags & PT_FLAG_NO_NEE) && sc.num_lights > 0) {
+        PtLight lt = sc.lights[pt_pick_light(sc.lights, sc.num_lights, u0)];
+        float su = pt_sqrt(u1);
+        float b1 = 1.0f - su, b2 = u2 * su;
+        pt_v3 le1 = pt_mk(lt.e1x, lt.e1y, lt.e1z), le2 = pt_mk(lt.e2x, lt.e2y, lt.e2z);
+        pt_v3 pl = pt_madd(pt_madd(pt_mk(lt.v0x, lt.v0y, lt.v0z), b1, le1), b2, le2);
+        pt_v3 wu = pt_sub(pl, po);
+        float d2 = pt_dot(wu, wu);
+        float inv_d = pt_div(1.0f, pt_sqrt(d2));
+        pt_v3 wi_w = pt_scale(wu, inv_d);
+        pt_v3 nl = pt_normalize(pt_cross(le1, le2));
+        float cl = -pt_dot(nl, wi_w);
+        float cs = pt_dot(n, wi_w);
+        if (cl > 0.0f && cs > 0.0f && d2 > 0.0f) {
+            pt_v3 wi = pt_mk(pt_dot(wi_w, T), pt_dot(wi_w, B), cs);
+            pt_v3 f; float pb;
+            pt_bsdf_eval(bsdf, wo, wi, &f, &pb);
+            float plight = pt_div(d2, cl * sc.light_area);
+            float w = pt_div(plight * plight, pt_fma(plight, plight, pb * pb));
+            float g = pt_div(cs * w, plight);
+            sh->o = po; sh->d = wu; sh->tmax = 0.999f;
+            sh->contrib = pt_mk(path->beta.x * f.x * lt.emr * g, path->beta.y * f.y * lt.emg * g, path->beta.z * f.z * lt.emb * g);
+            sh->valid = true;
+        }
+    }
+
+    // B3: BSDF sample
+    float u3 = pt_rng_f(&path->rng), u4 = pt_rng_f(&path->rng), u5 = pt_rng_f(&path->rng), u6 = pt_rng_f(&path->rng);
+    pt_v3 wi;
+    if (!pt_bsdf_sample(bsdf, wo, u3, u4, u5, &wi)) return false;
+    pt_v3 f; float pdf;
+    pt_bsdf_eval(bsdf, wo, wi, &f, &pdf);
+    if (!(pdf > 0.0f)) return false;
+    float g = pt_div(wi.z, pdf);
+    path->beta = pt_mk(path->beta.x * f.x * g, path->beta.y * f.y * g, path->beta.z * f.z * g);
+    if (path->bounce >= 2) {  // Russian roulette
+        float q = pt_min(pt_maxcomp(path->beta), 0.95f);
+        if (!(u6 < q)) return false;
+        float iq = pt_div(1.0f, q);
+        path->beta = pt_scale(path->beta, iq);
+    }
+    if (!(pt_maxcomp(path->beta) > 0.0f)) return false;
+    path->o = po;
+    path->d = pt_normalize(pt_madd(pt_madd(pt_scale(T, wi.x), wi.y, B), wi.z, n));
+    path->pdf_prev = pdf;
+    path->bounce += 1;
+    return true;
+}
+
+PT_HD void pt_shade_miss(PtPath* path, const PtShadeConsts& sc) {
+    path->L = pt_mk(pt_fma(path->beta.x, sc.bg[0], path->L.x), pt_fma(path->beta.y, sc.bg[1], path->L.y), pt_fma(path->beta.z, sc.bg[2], path->L.z));
+}

@@ -1,0 +1,203 @@
+/* foundation_pt.h — C ABI of the B200-native path-tracing backend for Foundation's src/Renderer.
+ *
+ * Plain C99: opaque context, POD descriptor structs with a leading struct_size, explicit byte sizes and
+ * strides, int32 status returns (0 = OK, negative = error class; text via foundation_pt_last_error).
+ * Nothing here throws, aborts, or exposes a torch / CUDA type.  Each entry cites the reference
+ * interface it stands in for (paths relative to mos9527/Foundation); where the reference has no
+ * counterpart (it ships no ray tracer — SURVEY.md §0) the citation is the slot in src/Renderer the
+ * call occupies.
+ *
+ * Conventions taken from the reference:
+ *   - matrices are column-major float[16], exactly `struct uniform_buffer` (src/Renderer/Renderer.cpp:28-33);
+ *   - world is Z-up, right-handed; clip space is Vulkan's with the Y flip `proj[1][1] *= -1`
+ *     (Renderer.cpp:373-380), so pixel (0,0) is the top-left corner;
+ *   - vertex data arrives as R32G32B32_SIGNED_FLOAT with an explicit byte stride, indices as R16_UINT or
+ *     R32_UINT (src/Platform/RHI/Common.hpp:18-27; index switch src/Platform/RHI/Vulkan/Command.cpp:292-302);
+ *   - the colour target is R8G8B8A8_UNORM 1920x1080 (Renderer.cpp:40-41);
+ *   - uploads are blocking and input pointers are borrowed only for the duration of the call, like the
+ *     staging uploads at Renderer.cpp:133-197;
+ *   - a context is single-caller (the reference is single-threaded) and calls return after the GPU work
+ *     is complete, like Renderer::Draw (Renderer.cpp:394).
+ */
+#ifndef FOUNDATION_PT_H
+#define FOUNDATION_PT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define FOUNDATION_PT_API __declspec(dllexport)
+#else
+#define FOUNDATION_PT_API __attribute__((visibility("default")))
+#endif
+
+typedef struct foundation_pt_context foundation_pt_context;
+
+/* status codes */
+enum {
+    FOUNDATION_PT_OK = 0,
+    FOUNDATION_PT_ERR_ARGUMENT = -1,   /* bad pointer / size / enum / struct_size                       */
+    FOUNDATION_PT_ERR_STATE = -2,      /* call order (e.g. render before scene_commit)                  */
+    FOUNDATION_PT_ERR_CUDA = -3,       /* a CUDA runtime call failed; text has the cudaError string     */
+    FOUNDATION_PT_ERR_OOM = -4,        /* host or device allocation failed                              */
+    FOUNDATION_PT_ERR_NO_DEVICE = -5,  /* no CUDA device: there is deliberately NO CPU fallback         */
+    FOUNDATION_PT_ERR_UNSUPPORTED = -6
+};
+
+/* Index formats: values mirror RHIResourceFormat usage at Vulkan/Command.cpp:292-302. */
+enum { FOUNDATION_PT_INDEX_U16 = 16, FOUNDATION_PT_INDEX_U32 = 32, FOUNDATION_PT_INDEX_NONE = 0 /* unindexed soup */ };
+
+/* Host-scratch allocation callbacks: same (user, size, alignment) triple as the reference's only extern "C"
+ * precedent, vkCustomCpuAllocation / vkCustomCpuFree over Core::Allocator
+ * (src/Platform/RHI/Vulkan/Application.hpp:11-26, Application.cpp:93-110).  May be NULL (malloc/free). */
+typedef struct foundation_pt_allocator {
+    void* user;
+    void* (*alloc)(void* user, size_t size, size_t alignment);
+    void (*free)(void* user, void* ptr);
+} foundation_pt_allocator;
+
+typedef struct foundation_pt_config {
+    uint32_t struct_size;   /* = sizeof(foundation_pt_config)                                           */
+    int32_t device;         /* CUDA device ordinal; the reference takes EnumerateDevices()[0] (Editor.cpp:18) */
+    uint32_t width, height; /* render target; reference: swapchain extent 1920x1080 (Renderer.cpp:41)   */
+    uint64_t seed;          /* PCG stream seed for the progressive render                                */
+    uint32_t max_leaf_tris; /* 1..3 triangles per BVH8 leaf slot (0 = default 3)                        */
+    uint32_t flags;         /* FOUNDATION_PT_FLAG_*                                                      */
+    float background[3];    /* constant environment radiance returned on a miss                          */
+    uint32_t reserved;
+} foundation_pt_config;
+
+enum {
+    FOUNDATION_PT_FLAG_NO_MATERIAL_SORT = 1u << 0, /* skip the counting sort by material between bounces (A/B) */
+    FOUNDATION_PT_FLAG_NO_NEE = 1u << 1,           /* BSDF sampling only (oracle self-checks)                  */
+    FOUNDATION_PT_FLAG_NO_BSDF_EMISSION = 1u << 2  /* NEE only: emitters hit by BSDF rays after bounce 0 add nothing */
+};
+
+/* Material: a two-lobe "diffuse + GGX" surface and an emitter.  32 bytes. */
+typedef struct foundation_pt_material {
+    float base_color[3];
+    float roughness;   /* GGX alpha = roughness^2, clamped to >= 1e-3 */
+    float emission[3]; /* radiance leaving the front side (geometric normal side) */
+    float metallic;    /* 0: Lambert(base) + dielectric GGX coat F0=0.04; 1: conductor GGX F0=base_color */
+} foundation_pt_material;
+
+/* Instance: mesh id + 3x4 object->world, row-major rows [m00 m01 m02 tx] (the affine part of a glm::mat4
+ * model matrix such as the one Renderer::Draw animates at Renderer.cpp:373, transposed to rows). 64 bytes. */
+typedef struct foundation_pt_instance {
+    uint32_t mesh_id;
+    uint32_t reserved[3];
+    float transform[12];
+} foundation_pt_instance;
+
+/* Ray and hit records of the parity / bench interface.  32 and 16 (+4) bytes, the SoA element sizes that
+ * SURVEY.md §8(d)'s algorithmic-bytes formula counts. */
+typedef struct foundation_pt_ray {
+    float origin[3];
+    float tmin;
+    float direction[3]; /* need not be normalised; t is in units of |direction| */
+    float tmax;         /* exclusive; +inf for unbounded */
+} foundation_pt_ray;
+
+typedef struct foundation_pt_hit {
+    float t;            /* +inf on a miss */
+    float u, v;         /* barycentrics of the hit (weights of vertex 1 and 2) */
+    uint32_t prim;      /* triangle index inside its mesh (as passed to mesh_create); 0xFFFFFFFF on a miss */
+} foundation_pt_hit;
+
+typedef struct foundation_pt_build_stats {
+    uint32_t struct_size;
+    uint32_t num_meshes, num_instances;
+    uint64_t num_triangles;       /* sum over meshes (unique) */
+    uint64_t effective_triangles; /* sum over instances */
+    uint64_t num_nodes8;          /* BVH8 nodes over all BLAS + TLAS */
+    uint64_t device_bytes;        /* nodes + triangles resident in HBM */
+    float build_ms;               /* device time of A1..A6 (CUDA events) */
+    float sort_ms;                /* of which: radix sort */
+    float scene_lo[3], scene_hi[3];
+} foundation_pt_build_stats;
+
+typedef struct foundation_pt_stats {
+    uint32_t struct_size;
+    uint32_t kernel_launches;  /* kernels of THIS library launched by the last render/trace call */
+    uint64_t rays_extend;      /* closest-hit rays traced by the last render call */
+    uint64_t rays_shadow;      /* any-hit rays traced by the last render call */
+    float last_ms;             /* device time of the last render/trace call (CUDA events on the context's stream) */
+    float trace_ms;            /* of which traversal kernels */
+    float shade_ms;            /* of which shading / sorting / compaction kernels */
+    uint32_t reserved;
+    uint64_t total_launches;   /* since create */
+} foundation_pt_stats;
+
+/* ---- lifetime (reference slot: Renderer::Renderer / ~Renderer, src/Renderer/Renderer.cpp:34-311, 402-406) ---- */
+FOUNDATION_PT_API int32_t foundation_pt_create(const foundation_pt_config* config, const foundation_pt_allocator* host_alloc,
+                                               foundation_pt_context** out_ctx);
+FOUNDATION_PT_API int32_t foundation_pt_destroy(foundation_pt_context* ctx);
+/* Never NULL. ctx may be NULL (returns the message of the last failed create on this thread). */
+FOUNDATION_PT_API const char* foundation_pt_last_error(const foundation_pt_context* ctx);
+
+/* ---- scene upload (reference slot: the blocking vertex/index staging uploads, Renderer.cpp:133-197) ---- */
+FOUNDATION_PT_API int32_t foundation_pt_materials_set(foundation_pt_context* ctx, const foundation_pt_material* materials, uint32_t count);
+/* positions: float3 at `pos_stride_bytes` intervals (the reference's vertex_input is over-aligned by glm,
+ * Renderer.cpp:23-27,110-115 — hence the explicit stride).  indices: 3 per triangle, or NULL with
+ * INDEX_NONE (3 consecutive vertices per triangle).  material_ids: one uint32 per triangle or NULL (all 0). */
+FOUNDATION_PT_API int32_t foundation_pt_mesh_create(foundation_pt_context* ctx, const void* positions, size_t pos_stride_bytes,
+                                                    uint32_t num_vertices, const void* indices, uint32_t index_format,
+                                                    uint32_t num_triangles, const uint32_t* material_ids, uint32_t* out_mesh_id);
+/* Optional.  Without it every mesh is instanced once with the identity transform. */
+FOUNDATION_PT_API int32_t foundation_pt_instances_set(foundation_pt_context* ctx, const foundation_pt_instance* instances, uint32_t count);
+/* Builds every BLAS (Morton LBVH -> BVH8) and the TLAS on the device.  stats may be NULL. */
+FOUNDATION_PT_API int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_build_stats* stats);
+
+/* ---- camera (reference: uniform_buffer.view / .proj written each Draw, Renderer.cpp:372-380) ---- */
+FOUNDATION_PT_API int32_t foundation_pt_camera_set(foundation_pt_context* ctx, const float view[16], const float proj[16]);
+
+/* ---- multi-GPU partition: this context renders only the pixels of tiles k with (k + row rotation) % count == rank.
+ *      tile_size in pixels (0 = 32).  rank 0 / count 1 is the default (whole frame).  No reference counterpart:
+ *      the reference is single-device (Editor.cpp:18). ---- */
+FOUNDATION_PT_API int32_t foundation_pt_partition_set(foundation_pt_context* ctx, uint32_t rank, uint32_t count, uint32_t tile_size);
+
+/* ---- render (reference slot: Renderer::Record's pass body, Renderer.cpp:332-351, driven by Draw :367-401) ----
+ * Adds samples [sample_begin, sample_begin + sample_count) of every owned pixel to the accumulation buffer.
+ * sample_begin == 0 clears the buffer first. */
+FOUNDATION_PT_API int32_t foundation_pt_render(foundation_pt_context* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces);
+/* Linear radiance SUM (not yet divided by spp) as float4 per pixel, row-major from the top-left; w = sample count. */
+FOUNDATION_PT_API int32_t foundation_pt_read_accum(foundation_pt_context* ctx, float* rgba, size_t size_bytes);
+/* accum / spp, clamped to [0,1], packed R8G8B8A8_UNORM (the reference's swapchain format, Renderer.cpp:40). */
+FOUNDATION_PT_API int32_t foundation_pt_resolve_rgba8(foundation_pt_context* ctx, uint8_t* rgba8, size_t size_bytes);
+/* Device address of the accumulation buffer (width*height float4) for zero-copy hand-off to a collective
+ * (torch.distributed / NCCL reduce in foundation_b200.distributed).  Valid until destroy. */
+FOUNDATION_PT_API int32_t foundation_pt_accum_device_ptr(foundation_pt_context* ctx, void** out_device_ptr, size_t* out_size_bytes);
+
+/* ---- parity / bench interface on explicit ray sets (no reference counterpart) ----
+ * Host buffers: copies are inside the call (this is the `e2e` path of bench.py).  out_inst may be NULL. */
+FOUNDATION_PT_API int32_t foundation_pt_trace_closest(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count,
+                                                      foundation_pt_hit* out_hits, uint32_t* out_inst);
+FOUNDATION_PT_API int32_t foundation_pt_trace_any(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count, uint8_t* out_occluded);
+/* Device-resident ray sets: upload once, trace many times (this is the `value` path of bench.py). */
+FOUNDATION_PT_API int32_t foundation_pt_rays_upload(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count);
+FOUNDATION_PT_API int32_t foundation_pt_rays_trace_closest(foundation_pt_context* ctx, uint64_t first, uint64_t count);
+FOUNDATION_PT_API int32_t foundation_pt_rays_trace_any(foundation_pt_context* ctx, uint64_t first, uint64_t count);
+FOUNDATION_PT_API int32_t foundation_pt_rays_download_hits(foundation_pt_context* ctx, uint64_t first, uint64_t count,
+                                                           foundation_pt_hit* out_hits, uint32_t* out_inst);
+/* Exhaustive O(rays x triangles) closest hit on the device — ground truth that uses no BVH (test utility). */
+FOUNDATION_PT_API int32_t foundation_pt_rays_trace_brute(foundation_pt_context* ctx, uint64_t first, uint64_t count);
+
+/* ---- introspection ---- */
+FOUNDATION_PT_API int32_t foundation_pt_stats_get(foundation_pt_context* ctx, foundation_pt_stats* stats);
+/* Copies the device-built acceleration structure of one mesh back to the host so tests can compare it
+ * byte-for-byte with the oracle's build.  Any pointer may be NULL; counts are always written.
+ * nodes: 80 bytes each; tris: 48 bytes each; order: uint32 per triangle (sorted position -> input triangle). */
+FOUNDATION_PT_API int32_t foundation_pt_blas_download(foundation_pt_context* ctx, uint32_t mesh_id, void* nodes, size_t nodes_bytes,
+                                                      void* tris, size_t tris_bytes, uint32_t* order, size_t order_bytes,
+                                                      uint64_t* out_num_nodes, uint64_t* out_num_tris);
+FOUNDATION_PT_API int32_t foundation_pt_tlas_download(foundation_pt_context* ctx, void* nodes, size_t nodes_bytes, uint32_t* order,
+                                                      size_t order_bytes, uint64_t* out_num_nodes, uint64_t* out_num_instances);
+FOUNDATION_PT_API uint32_t foundation_pt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOUNDATION_PT_H */
