@@ -1,0 +1,839 @@
+// foundation_pt.cu — the C ABI (include/foundation_pt.h) over the sm_100a kernels in pt_kernels.cuh.
+// Host side of the drop-in boundary: context + scene upload (the slot of Renderer::Renderer's blocking
+// staging uploads, mos9527/Foundation src/Renderer/Renderer.cpp:133-197), acceleration-structure build,
+// the wavefront render loop (the slot of Renderer::Record's pass body, Renderer.cpp:332-351) and the
+// explicit-ray-set interface used for parity and the Mrays/s metric.
+// There is NO CPU fallback: without a CUDA device foundation_pt_create fails with FOUNDATION_PT_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/foundation_pt.h"
+#include "pt_kernels.cuh"
+
+static_assert(sizeof(foundation_pt_ray) == 32 && sizeof(foundation_pt_hit) == 16, "ABI record sizes");
+static_assert(sizeof(foundation_pt_material) == sizeof(PtMaterial) && sizeof(PtMaterial) == 32, "material layout");
+static_assert(sizeof(PtInstance) == 112 && sizeof(PtTri) == 48 && sizeof(PtLight) == 64, "device record sizes");
+static_assert(sizeof(foundation_pt_instance) == 64, "instance ABI size");
+
+namespace {
+
+thread_local std::string g_create_error = "no error";
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    cudaError_t alloc(size_t n) { release(); if (n == 0) n = 16; cudaError_t e = cudaMalloc(&p, n); if (e == cudaSuccess) bytes = n; else p = nullptr; return e; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Mesh {
+    // host copies (light extraction, validation)
+    std::vector<uint8_t> h_pos; std::vector<uint8_t> h_idx; std::vector<uint32_t> h_mat;
+    uint32_t stride = 0, idx_fmt = 0, nverts = 0, ntris = 0;
+    DevBuf d_pos, d_idx, d_mat;
+    // build products
+    DevBuf d_nodes, d_tris, d_order;
+    uint32_t num_nodes = 0;
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, pad = 0;
+    PtMeshRaw raw() const { PtMeshRaw r; r.pos = d_pos.as<uint8_t>(); r.stride = stride; r.idx = d_idx.p; r.idx_fmt = idx_fmt; r.ntris = ntris; r.mat = d_mat.as<uint32_t>(); return r; }
+    void host_tri(uint32_t i, float* v9) const {
+        uint32_t id[3];
+        for (int k = 0; k < 3; ++k) {
+            if (idx_fmt == 32) id[k] = reinterpret_cast<const uint32_t*>(h_idx.data())[3 * (size_t)i + k];
+            else if (idx_fmt == 16) id[k] = reinterpret_cast<const uint16_t*>(h_idx.data())[3 * (size_t)i + k];
+            else id[k] = 3 * i + k;
+            memcpy(v9 + 3 * k, h_pos.data() + (size_t)id[k] * stride, 12);
+        }
+    }
+};
+
+}  // namespace
+
+struct foundation_pt_context {
+    foundation_pt_config cfg{};
+    foundation_pt_allocator host_alloc{};
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    mutable std::string err = "no error";
+
+    std::vector<Mesh> meshes;
+    std::vector<PtMaterial> mats;
+    std::vector<foundation_pt_instance> insts; bool has_insts = false;
+
+    // committed scene
+    bool committed = false, two_level = false;
+    DevBuf d_nodes_all, d_tris_all, d_instances, d_inst_in, d_mesh_info, d_mats, d_lights;
+    std::vector<PtMeshInfo> mesh_info;
+    DevBuf d_tlas_order; uint32_t tlas_nodes = 0, num_inst = 0;
+    PtSceneView view{};
+    uint32_t num_lights = 0; float light_area = 0, ray_eps = 0;
+    float wlo[3] = {0, 0, 0}, whi[3] = {0, 0, 0};
+    foundation_pt_build_stats bstats{};
+
+    PtCamera cam{}; bool cam_set = false;
+
+    // wavefront state
+    uint32_t part_rank = 0, part_count = 1, part_tile = 32;
+    bool wave_ready = false;
+    DevBuf w_ray_o, w_ray_d, w_beta, w_L, w_rng, w_hit, w_active, w_next, w_sorted, w_sh_o, w_sh_d, w_sh_c, w_slot_pixel, w_ctr, w_keyhist, d_accum;
+    uint32_t num_slots = 0;
+    DevBuf d_status, d_counters;
+
+    // explicit ray set
+    DevBuf d_rays, d_hits, d_hit_inst, d_occ; uint64_t num_rays = 0;
+
+    foundation_pt_stats stats{};
+    uint64_t total_launches = 0; uint32_t call_launches = 0;
+
+    int32_t fail(int32_t code, const std::string& msg) const { err = msg; return code; }
+};
+
+namespace {
+
+typedef foundation_pt_context Ctx;
+
+#define PT_CK(expr)                                                                                            \
+    do {                                                                                                       \
+        cudaError_t e_ = (expr);                                                                               \
+        if (e_ != cudaSuccess)                                                                                 \
+            return ctx->fail(e_ == cudaErrorMemoryAllocation ? FOUNDATION_PT_ERR_OOM : FOUNDATION_PT_ERR_CUDA, \
+                             std::string(#expr) + ": " + cudaGetErrorString(e_));                              \
+    } while (0)
+
+#define PT_LAUNCH(ctx, kernel, grid, block, ...)                        \
+    do {                                                                \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);     \
+        (ctx)->call_launches++; (ctx)->total_launches++;                \
+    } while (0)
+
+inline uint32_t grid_for(const Ctx* ctx, uint64_t n, uint32_t block, uint32_t blocks_per_sm) {
+    uint64_t need = (n + block - 1) / block;
+    uint64_t cap = (uint64_t)ctx->num_sms * blocks_per_sm;
+    if (need < 1) need = 1;
+    return (uint32_t)(need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device exclusive scan (in place allowed); total written to d_total (device uint32) if non-null
+// ------------------------------------------------------------------------------------------------
+int32_t scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf& chunk_sums, uint32_t* d_total) {
+    uint32_t chunks = (n + PT_SCAN_CHUNK - 1) / PT_SCAN_CHUNK;
+    if (chunks == 0) chunks = 1;
+    if (chunk_sums.bytes < (size_t)chunks * 4) PT_CK(chunk_sums.alloc((size_t)chunks * 4 + 1024));
+    PT_LAUNCH(ctx, k_scan_chunks, chunks, PT_SCAN_THREADS, in, out, n, chunk_sums.as<uint32_t>());
+    PT_LAUNCH(ctx, k_scan_sums, 1, 1024, chunk_sums.as<uint32_t>(), chunks, d_total);
+    if (chunks > 1) PT_LAUNCH(ctx, k_scan_add, chunks, PT_SCAN_THREADS, out, n, chunk_sums.as<uint32_t>());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A2: radix sort driver. keys/vals end up in (keys_a, vals_a) (8 passes = even number of swaps).
+// ------------------------------------------------------------------------------------------------
+int32_t radix_sort(Ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, DevBuf& hist, DevBuf& chunk_sums) {
+    uint32_t tiles = (n + PT_RS_TILE - 1) / PT_RS_TILE;
+    if (tiles == 0) return 0;
+    if (hist.bytes < (size_t)tiles * 256 * 4) PT_CK(hist.alloc((size_t)tiles * 256 * 4));
+    for (int pass = 0; pass < 8; ++pass) {
+        int shift = 8 * pass;
+        PT_LAUNCH(ctx, k_rs_hist, tiles, PT_RS_THREADS, keys_a, n, shift, hist.as<uint32_t>(), tiles);
+        int32_t rc = scan_u32(ctx, hist.as<uint32_t>(), hist.as<uint32_t>(), tiles * 256, chunk_sums, nullptr);
+        if (rc) return rc;
+        PT_LAUNCH(ctx, k_rs_scatter, tiles, PT_RS_THREADS, keys_a, vals_a, keys_b, vals_b, n, shift, hist.as<uint32_t>(), tiles);
+        std::swap(keys_a, keys_b); std::swap(vals_a, vals_b);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic LBVH -> BVH8 build over n primitives whose boxes are in d_prim_box and whose Morton keys are
+// already in (keys, vals).  Outputs: nodes (exact size), leaf_seq (n), order (n) = sorted vals.
+// ------------------------------------------------------------------------------------------------
+struct BuildOut { DevBuf nodes, leaf_seq, order; uint32_t num_nodes = 0; float sort_ms = 0; };
+
+int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, DevBuf& vals, const PtBuildParams* d_bp, uint32_t max_leaf, BuildOut* out) {
+    DevBuf keys_b, vals_b, hist, chunk_sums;
+    PT_CK(keys_b.alloc((size_t)n * 8)); PT_CK(vals_b.alloc((size_t)n * 4));
+    PT_CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    int32_t rc = radix_sort(ctx, keys.as<uint64_t>(), vals.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), n, hist, chunk_sums);
+    if (rc) return rc;
+    PT_CK(cudaEventRecord(ctx->ev3, ctx->stream));
+    keys_b.release(); vals_b.release(); hist.release();
+    // BVH2
+    DevBuf left, right, first, last, parent, box, flags;
+    size_t ni = n > 1 ? n - 1 : 1;
+    PT_CK(left.alloc(ni * 4)); PT_CK(right.alloc(ni * 4)); PT_CK(first.alloc(ni * 4)); PT_CK(last.alloc(ni * 4));
+    PT_CK(parent.alloc((2 * (size_t)n) * 4)); PT_CK(box.alloc((2 * (size_t)n) * sizeof(PtBox))); PT_CK(flags.alloc(ni * 4));
+    PT_CK(cudaMemsetAsync(flags.p, 0, ni * 4, ctx->stream));
+    PtBvh2 b; b.n = n; b.left = left.as<uint32_t>(); b.right = right.as<uint32_t>(); b.first = first.as<uint32_t>(); b.last = last.as<uint32_t>();
+    b.parent = parent.as<uint32_t>(); b.box = box.as<PtBox>();
+    if (n > 1) PT_LAUNCH(ctx, k_karras, grid_for(ctx, n - 1, 256, 8), 256, keys.as<uint64_t>(), b);
+    PT_LAUNCH(ctx, k_refit, grid_for(ctx, n, 256, 8), 256, b, d_prim_box, vals.as<uint32_t>(), flags.as<uint32_t>());
+    // collapse, level by level
+    DevBuf nodes_tmp, refs_a, refs_b, slots, n_int, n_prim, totals;
+    PT_CK(nodes_tmp.alloc((size_t)n * sizeof(PtNode8)));
+    PT_CK(refs_a.alloc((size_t)n * 4)); PT_CK(refs_b.alloc((size_t)n * 4));
+    PT_CK(out->leaf_seq.alloc((size_t)n * 4));
+    PT_CK(totals.alloc(16));
+    uint32_t zero = 0;
+    PT_CK(cudaMemcpyAsync(refs_a.p, &zero, 4, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t m = 1, level_start = 0, prim_total = 0;
+    size_t cap = 0;
+    while (m > 0) {
+        if (cap < m) {
+            cap = (size_t)m + m / 2 + 64;
+            PT_CK(slots.alloc(cap * 32)); PT_CK(n_int.alloc(cap * 4)); PT_CK(n_prim.alloc(cap * 4));
+        }
+        if ((uint64_t)level_start + m > n) return ctx->fail(FOUNDATION_PT_ERR_STATE, "BVH8 collapse exceeded node capacity");
+        PT_LAUNCH(ctx, k_collapse_select, grid_for(ctx, m, 128, 16), 128, b, refs_a.as<uint32_t>(), m, max_leaf, slots.as<uint32_t>(), n_int.as<uint32_t>(),
+                  n_prim.as<uint32_t>());
+        rc = scan_u32(ctx, n_int.as<uint32_t>(), n_int.as<uint32_t>(), m, chunk_sums, totals.as<uint32_t>());
+        if (rc) return rc;
+        rc = scan_u32(ctx, n_prim.as<uint32_t>(), n_prim.as<uint32_t>(), m, chunk_sums, totals.as<uint32_t>() + 1);
+        if (rc) return rc;
+        uint32_t next_start = level_start + m;
+        PT_LAUNCH(ctx, k_collapse_emit, grid_for(ctx, m, 128, 16), 128, b, refs_a.as<uint32_t>(), m, max_leaf, d_bp, slots.as<uint32_t>(), n_int.as<uint32_t>(),
+                  n_prim.as<uint32_t>(), level_start, next_start, prim_total, nodes_tmp.as<PtNode8>(), refs_b.as<uint32_t>(), out->leaf_seq.as<uint32_t>());
+        uint32_t tot[2];
+        PT_CK(cudaMemcpyAsync(tot, totals.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PT_CK(cudaStreamSynchronize(ctx->stream));
+        prim_total += tot[1]; level_start = next_start; m = tot[0];
+        std::swap(refs_a, refs_b);
+    }
+    if (prim_total != n) return ctx->fail(FOUNDATION_PT_ERR_STATE, "BVH8 collapse lost primitives");
+    out->num_nodes = level_start;
+    PT_CK(out->nodes.alloc((size_t)level_start * sizeof(PtNode8)));
+    PT_CK(cudaMemcpyAsync(out->nodes.p, nodes_tmp.p, (size_t)level_start * sizeof(PtNode8), cudaMemcpyDeviceToDevice, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); out->sort_ms = ms;
+    out->order = std::move(vals);
+    return 0;
+}
+
+int32_t build_blas(Ctx* ctx, Mesh& m, float* sort_ms) {
+    uint32_t n = m.ntris;
+    DevBuf prim_box, bounds, bp, keys, vals;
+    PT_CK(prim_box.alloc((size_t)n * sizeof(PtBox))); PT_CK(bounds.alloc(32)); PT_CK(bp.alloc(sizeof(PtBuildParams)));
+    PT_CK(keys.alloc((size_t)n * 8)); PT_CK(vals.alloc((size_t)n * 4));
+    uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    PT_CK(cudaMemcpyAsync(bounds.p, init, 24, cudaMemcpyHostToDevice, ctx->stream));
+    PtMeshRaw raw = m.raw();
+    PT_LAUNCH(ctx, k_tri_boxes, grid_for(ctx, n, 256, 8), 256, raw, prim_box.as<PtBox>(), bounds.as<uint32_t>());
+    PT_LAUNCH(ctx, k_build_params, 1, 32, bounds.as<uint32_t>(), bp.as<PtBuildParams>());
+    PT_LAUNCH(ctx, k_morton_tris, grid_for(ctx, n, 256, 8), 256, raw, bp.as<PtBuildParams>(), keys.as<uint64_t>(), vals.as<uint32_t>());
+    BuildOut out;
+    int32_t rc = build_bvh8(ctx, n, prim_box.as<PtBox>(), keys, vals, bp.as<PtBuildParams>(), ctx->cfg.max_leaf_tris, &out);
+    if (rc) return rc;
+    PT_CK(m.d_tris.alloc((size_t)n * sizeof(PtTri)));
+    PT_LAUNCH(ctx, k_write_tris, grid_for(ctx, n, 256, 8), 256, raw, out.order.as<uint32_t>(), out.leaf_seq.as<uint32_t>(), m.d_tris.as<PtTri>());
+    PtBuildParams hbp;
+    PT_CK(cudaMemcpyAsync(&hbp, bp.p, sizeof hbp, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(m.lo, hbp.lo, 12); memcpy(m.hi, hbp.hi, 12); m.pad = hbp.pad;
+    m.d_nodes = std::move(out.nodes); m.num_nodes = out.num_nodes; m.d_order = std::move(out.order);
+    *sort_ms += out.sort_ms;
+    return 0;
+}
+
+int32_t ensure_status(Ctx* ctx) {
+    if (!ctx->d_status.p) {
+        PT_CK(ctx->d_status.alloc(16)); PT_CK(ctx->d_counters.alloc(sizeof(PtDevCounters)));
+        PT_CK(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
+    }
+    return 0;
+}
+int32_t check_status(Ctx* ctx) {
+    uint32_t st = 0;
+    PT_CK(cudaMemcpyAsync(&st, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    if (st) { cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream); return ctx->fail(FOUNDATION_PT_ERR_STATE, "traversal stack overflow (PT_STACK_SIZE)"); }
+    return 0;
+}
+
+template <bool ANY>
+int32_t launch_trace(Ctx* ctx, const float4* rays, uint64_t n, float4* hits, uint32_t* inst, uint8_t* occ) {
+    if (n == 0) return 0;
+    int per_sm = 8;
+    uint32_t grid = grid_for(ctx, n, 128, per_sm);
+    if (ctx->two_level) PT_LAUNCH(ctx, (k_trace_rays<ANY, true, false>), grid, 128, ctx->view, rays, (unsigned long long)n, hits, inst, occ, ctx->d_status.as<uint32_t>(), nullptr);
+    else PT_LAUNCH(ctx, (k_trace_rays<ANY, false, false>), grid, 128, ctx->view, rays, (unsigned long long)n, hits, inst, occ, ctx->d_status.as<uint32_t>(), nullptr);
+    PT_CK(cudaGetLastError());
+    return 0;
+}
+
+void begin_call(Ctx* ctx) { ctx->call_launches = 0; cudaEventRecord(ctx->ev0, ctx->stream); }
+int32_t end_call(Ctx* ctx) {
+    PT_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.last_ms = ms; ctx->stats.kernel_launches = ctx->call_launches; ctx->stats.total_launches = ctx->total_launches;
+    return 0;
+}
+
+int32_t setup_wave(Ctx* ctx) {
+    if (ctx->wave_ready) return 0;
+    uint32_t W = ctx->cfg.width, H = ctx->cfg.height;
+    std::vector<uint32_t> slot_pixel;
+    bool whole = ctx->part_count <= 1;
+    if (!whole) {
+        uint32_t T = ctx->part_tile ? ctx->part_tile : 32;
+        for (uint32_t y = 0; y < H; ++y)
+            for (uint32_t x = 0; x < W; ++x)
+                if (((x / T) + (y / T)) % ctx->part_count == ctx->part_rank) slot_pixel.push_back(y * W + x);
+        ctx->num_slots = (uint32_t)slot_pixel.size();
+        PT_CK(ctx->w_slot_pixel.alloc((size_t)ctx->num_slots * 4));
+        PT_CK(cudaMemcpyAsync(ctx->w_slot_pixel.p, slot_pixel.data(), (size_t)ctx->num_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+        PT_CK(cudaStreamSynchronize(ctx->stream));
+    } else { ctx->num_slots = W * H; ctx->w_slot_pixel.release(); }
+    size_t S = ctx->num_slots ? ctx->num_slots : 1;
+    PT_CK(ctx->w_ray_o.alloc(S * 16)); PT_CK(ctx->w_ray_d.alloc(S * 16)); PT_CK(ctx->w_beta.alloc(S * 16)); PT_CK(ctx->w_L.alloc(S * 16));
+    PT_CK(ctx->w_rng.alloc(S * 16)); PT_CK(ctx->w_hit.alloc(S * 16)); PT_CK(ctx->w_active.alloc(S * 4)); PT_CK(ctx->w_next.alloc(S * 4));
+    PT_CK(ctx->w_sorted.alloc(S * 4)); PT_CK(ctx->w_sh_o.alloc(S * 16)); PT_CK(ctx->w_sh_d.alloc(S * 16)); PT_CK(ctx->w_sh_c.alloc(S * 16));
+    PT_CK(ctx->w_ctr.alloc(sizeof(PtWaveCounters))); PT_CK(ctx->w_keyhist.alloc((PT_KEY_BUCKETS + 1) * 4));
+    PT_CK(cudaMemsetAsync(ctx->w_ctr.p, 0, sizeof(PtWaveCounters), ctx->stream));
+    if (!ctx->d_accum.p) {
+        PT_CK(ctx->d_accum.alloc((size_t)W * H * 16));
+        PT_CK(cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)W * H * 16, ctx->stream));
+    }
+    ctx->wave_ready = true;
+    return 0;
+}
+
+template <bool TWO>
+int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
+    PtWave w;
+    w.ray_o = ctx->w_ray_o.as<float4>(); w.ray_d = ctx->w_ray_d.as<float4>(); w.beta = ctx->w_beta.as<float4>(); w.L = ctx->w_L.as<float4>();
+    w.rng = ctx->w_rng.as<uint4>(); w.hit = ctx->w_hit.as<float4>(); w.active = ctx->w_active.as<uint32_t>(); w.next = ctx->w_next.as<uint32_t>();
+    w.sorted = ctx->w_sorted.as<uint32_t>(); w.sh_o = ctx->w_sh_o.as<float4>(); w.sh_d = ctx->w_sh_d.as<float4>(); w.sh_c = ctx->w_sh_c.as<float4>();
+    w.slot_pixel = ctx->part_count > 1 ? ctx->w_slot_pixel.as<uint32_t>() : nullptr;
+    w.ctr = ctx->w_ctr.as<PtWaveCounters>(); w.key_hist = ctx->w_keyhist.as<uint32_t>(); w.num_slots = ctx->num_slots;
+    PtShadeScene ss;
+    ss.sv = ctx->view; ss.mats = ctx->d_mats.as<PtMaterial>(); ss.num_mats = (uint32_t)ctx->mats.size();
+    ss.sc.lights = ctx->d_lights.as<PtLight>(); ss.sc.num_lights = ctx->num_lights; ss.sc.light_area = ctx->light_area; ss.sc.ray_eps = ctx->ray_eps;
+    ss.sc.flags = ctx->cfg.flags; ss.sc.max_bounces = max_bounces;
+    ss.sc.bg[0] = ctx->cfg.background[0]; ss.sc.bg[1] = ctx->cfg.background[1]; ss.sc.bg[2] = ctx->cfg.background[2];
+    const bool sort = !(ctx->cfg.flags & FOUNDATION_PT_FLAG_NO_MATERIAL_SORT);
+    const uint32_t S = ctx->num_slots;
+    const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8);
+    uint32_t* status = ctx->d_status.as<uint32_t>();
+    for (uint32_t smp = s0; smp < s0 + ns; ++smp) {
+        PtFrame f; f.cam = ctx->cam; f.seed = ctx->cfg.seed; f.width = ctx->cfg.width; f.height = ctx->cfg.height; f.sample = smp;
+        w.active = ctx->w_active.as<uint32_t>(); w.next = ctx->w_next.as<uint32_t>();
+        PT_LAUNCH(ctx, k_raygen, g256, 256, w, f);
+        for (uint32_t b = 0; b <= max_bounces; ++b) {
+            if (sort) PT_LAUNCH(ctx, k_key_clear, 2, 1024, w.key_hist);
+            PT_LAUNCH(ctx, k_extend<TWO>, g128, 128, ctx->view, w, status, sort ? 1 : 0);
+            const uint32_t* list = w.active;
+            if (sort) {
+                PT_LAUNCH(ctx, k_key_scan, 1, 1024, w.key_hist);
+                PT_LAUNCH(ctx, k_key_scatter, g256, 256, w);
+                list = w.sorted;
+            }
+            PT_LAUNCH(ctx, k_shade<TWO>, g128, 128, ss, w, list);
+            PT_LAUNCH(ctx, k_connect<TWO>, g128, 128, ctx->view, w, status);
+            PT_LAUNCH(ctx, k_bounce_end, 1, 32, w);
+            std::swap(w.active, w.next);
+        }
+        PT_LAUNCH(ctx, k_accumulate, g256, 256, w, ctx->d_accum.as<float4>());
+    }
+    PT_CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+#define PT_TRY try {
+#define PT_CATCH(ctxexpr)                                                                                               \
+    } catch (const std::bad_alloc&) { if (ctxexpr) (ctxexpr)->err = "host allocation failed"; return FOUNDATION_PT_ERR_OOM; } \
+    catch (const std::exception& e) { if (ctxexpr) (ctxexpr)->err = e.what(); return FOUNDATION_PT_ERR_STATE; }         \
+    catch (...) { if (ctxexpr) (ctxexpr)->err = "unknown exception"; return FOUNDATION_PT_ERR_STATE; }
+
+extern "C" {
+
+uint32_t foundation_pt_version(void) { return 0x00010000u; }
+
+const char* foundation_pt_last_error(const foundation_pt_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t foundation_pt_create(const foundation_pt_config* config, const foundation_pt_allocator* host_alloc, foundation_pt_context** out_ctx) {
+    if (!out_ctx) { g_create_error = "out_ctx is NULL"; return FOUNDATION_PT_ERR_ARGUMENT; }
+    *out_ctx = nullptr;
+    if (!config || config->struct_size != sizeof(foundation_pt_config)) { g_create_error = "config NULL or struct_size mismatch"; return FOUNDATION_PT_ERR_ARGUMENT; }
+    if (config->width == 0 || config->height == 0 || (uint64_t)config->width * config->height > (1ull << 30)) { g_create_error = "bad render target size"; return FOUNDATION_PT_ERR_ARGUMENT; }
+    if (config->max_leaf_tris > 3) { g_create_error = "max_leaf_tris must be 0..3"; return FOUNDATION_PT_ERR_ARGUMENT; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (") + cudaGetErrorString(e) + "); this backend has no CPU fallback";
+        cudaGetLastError();
+        return FOUNDATION_PT_ERR_NO_DEVICE;
+    }
+    if (config->device < 0 || config->device >= ndev) { g_create_error = "device ordinal out of range"; return FOUNDATION_PT_ERR_ARGUMENT; }
+    foundation_pt_context* ctx = new (std::nothrow) foundation_pt_context();
+    if (!ctx) { g_create_error = "host allocation failed"; return FOUNDATION_PT_ERR_OOM; }
+    ctx->cfg = *config;
+    if (ctx->cfg.max_leaf_tris == 0) ctx->cfg.max_leaf_tris = PT_MAX_LEAF;
+    if (host_alloc) ctx->host_alloc = *host_alloc;
+    ctx->device = config->device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev2)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev3)) != cudaSuccess) {
+        g_create_error = std::string("CUDA init failed: ") + cudaGetErrorString(e);
+        delete ctx;
+        return FOUNDATION_PT_ERR_CUDA;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->mats.push_back(PtMaterial{0.8f, 0.8f, 0.8f, 0.5f, 0, 0, 0, 0});
+    *out_ctx = ctx;
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_destroy(foundation_pt_context* ctx) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2); if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    cudaStream_t s1 = ctx->stream, s2 = ctx->stream2;
+    delete ctx;   // frees device buffers
+    if (s1) cudaStreamDestroy(s1); if (s2) cudaStreamDestroy(s2);
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_materials_set(foundation_pt_context* ctx, const foundation_pt_material* materials, uint32_t count) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!materials || count == 0) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "materials NULL or empty");
+    PT_TRY
+    ctx->mats.resize(count);
+    memcpy(ctx->mats.data(), materials, (size_t)count * 32);
+    ctx->committed = false;
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_mesh_create(foundation_pt_context* ctx, const void* positions, size_t pos_stride_bytes, uint32_t num_vertices, const void* indices,
+                                  uint32_t index_format, uint32_t num_triangles, const uint32_t* material_ids, uint32_t* out_mesh_id) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!positions || num_vertices == 0 || num_triangles == 0) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_create: empty mesh");
+    if (pos_stride_bytes < 12 || (pos_stride_bytes & 3) || pos_stride_bytes > 4096) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_create: stride must be a multiple of 4, >= 12");
+    if (index_format != FOUNDATION_PT_INDEX_U16 && index_format != FOUNDATION_PT_INDEX_U32 && index_format != FOUNDATION_PT_INDEX_NONE)
+        return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_create: index_format must be 16, 32 or 0");
+    if ((index_format != FOUNDATION_PT_INDEX_NONE) != (indices != nullptr)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_create: indices / index_format mismatch");
+    if (index_format == FOUNDATION_PT_INDEX_NONE && (uint64_t)num_triangles * 3 > num_vertices) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_create: not enough vertices");
+    if (num_triangles > 0x7fffffffu / 3) return ctx->fail(FOUNDATION_PT_ERR_UNSUPPORTED, "mesh_create: too many triangles in one mesh");
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    Mesh m;
+    m.stride = (uint32_t)pos_stride_bytes; m.idx_fmt = index_format; m.nverts = num_vertices; m.ntris = num_triangles;
+    size_t pos_bytes = (size_t)(num_vertices - 1) * pos_stride_bytes + 12;
+    m.h_pos.assign((const uint8_t*)positions, (const uint8_t*)positions + pos_bytes);
+    size_t idx_bytes = index_format ? (size_t)num_triangles * 3 * (index_format / 8) : 0;
+    if (idx_bytes) m.h_idx.assign((const uint8_t*)indices, (const uint8_t*)indices + idx_bytes);
+    // validate indices (the reference trusts its callers; a C ABI should not read out of bounds on the device)
+    for (size_t k = 0; k < (size_t)num_triangles * 3 && index_format; ++k) {
+        uint32_t v = index_format == 32 ? reinterpret_cast<const uint32_t*>(m.h_idx.data())[k] : reinterpret_cast<const uint16_t*>(m.h_idx.data())[k];
+        if (v >= num_vertices) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_create: index out of range");
+    }
+    m.h_mat.assign(num_triangles, 0u);
+    if (material_ids) memcpy(m.h_mat.data(), material_ids, (size_t)num_triangles * 4);
+    PT_CK(m.d_pos.alloc(pos_bytes + 16)); PT_CK(m.d_mat.alloc((size_t)num_triangles * 4));
+    PT_CK(cudaMemcpyAsync(m.d_pos.p, m.h_pos.data(), pos_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaMemcpyAsync(m.d_mat.p, m.h_mat.data(), (size_t)num_triangles * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (idx_bytes) { PT_CK(m.d_idx.alloc(idx_bytes)); PT_CK(cudaMemcpyAsync(m.d_idx.p, m.h_idx.data(), idx_bytes, cudaMemcpyHostToDevice, ctx->stream)); }
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    ctx->meshes.push_back(std::move(m));
+    if (out_mesh_id) *out_mesh_id = (uint32_t)ctx->meshes.size() - 1;
+    ctx->committed = false;
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_instances_set(foundation_pt_context* ctx, const foundation_pt_instance* instances, uint32_t count) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!instances || count == 0) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "instances NULL or empty");
+    PT_TRY
+    for (uint32_t i = 0; i < count; ++i) {
+        if (instances[i].mesh_id >= ctx->meshes.size()) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "instances_set: mesh_id out of range");
+        float w2o[12];
+        if (!pt_invert_affine(instances[i].transform, w2o)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "instances_set: singular transform");
+    }
+    ctx->insts.assign(instances, instances + count);
+    ctx->has_insts = true; ctx->committed = false;
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_build_stats* stats) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (ctx->meshes.empty()) return ctx->fail(FOUNDATION_PT_ERR_STATE, "scene_commit: no meshes");
+    if (stats && stats->struct_size != sizeof(foundation_pt_build_stats)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "build_stats struct_size mismatch");
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    ctx->call_launches = 0;
+    PT_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    float sort_ms = 0;
+    for (auto& m : ctx->meshes) {
+        if (m.d_nodes.p) continue;   // BLAS reuse: a mesh is immutable once created
+        int32_t rc = build_blas(ctx, m, &sort_ms);
+        if (rc) return rc;
+    }
+    ctx->two_level = ctx->has_insts || ctx->meshes.size() > 1;
+    uint64_t total_tris = 0, eff_tris = 0, total_nodes = 0;
+    for (auto& m : ctx->meshes) { total_tris += m.ntris; total_nodes += m.num_nodes; }
+    ctx->mesh_info.assign(ctx->meshes.size(), PtMeshInfo{});
+    std::vector<PtInstance> rec;
+    if (ctx->two_level) {
+        if (!ctx->has_insts) {
+            ctx->insts.resize(ctx->meshes.size());
+            for (size_t i = 0; i < ctx->meshes.size(); ++i) {
+                memset(&ctx->insts[i], 0, sizeof(foundation_pt_instance));
+                ctx->insts[i].mesh_id = (uint32_t)i;
+                ctx->insts[i].transform[0] = ctx->insts[i].transform[5] = ctx->insts[i].transform[10] = 1.0f;
+            }
+        }
+        uint32_t ni = (uint32_t)ctx->insts.size();
+        ctx->num_inst = ni;
+        rec.resize(ni);
+        for (uint32_t i = 0; i < ni; ++i) {
+            memcpy(rec[i].o2w, ctx->insts[i].transform, 48);
+            pt_invert_affine(rec[i].o2w, rec[i].w2o);
+            rec[i].mesh_id = ctx->insts[i].mesh_id; rec[i].inst_id = i; rec[i].node_base = rec[i].tri_base = 0;
+            eff_tris += ctx->meshes[rec[i].mesh_id].ntris;
+        }
+        for (size_t k = 0; k < ctx->meshes.size(); ++k) {
+            memcpy(ctx->mesh_info[k].lo, ctx->meshes[k].lo, 12); memcpy(ctx->mesh_info[k].hi, ctx->meshes[k].hi, 12);
+            ctx->mesh_info[k].pad = ctx->meshes[k].pad; ctx->mesh_info[k].ntris = ctx->meshes[k].ntris; ctx->mesh_info[k].nnodes = ctx->meshes[k].num_nodes;
+        }
+        PT_CK(ctx->d_inst_in.alloc((size_t)ni * sizeof(PtInstance))); PT_CK(ctx->d_mesh_info.alloc(ctx->mesh_info.size() * sizeof(PtMeshInfo)));
+        PT_CK(cudaMemcpyAsync(ctx->d_inst_in.p, rec.data(), (size_t)ni * sizeof(PtInstance), cudaMemcpyHostToDevice, ctx->stream));
+        PT_CK(cudaMemcpyAsync(ctx->d_mesh_info.p, ctx->mesh_info.data(), ctx->mesh_info.size() * sizeof(PtMeshInfo), cudaMemcpyHostToDevice, ctx->stream));
+        // A6: TLAS = the same LBVH -> BVH8 pipeline over instance world boxes, one instance per leaf slot
+        DevBuf prim_box, bounds, bp, keys, vals;
+        PT_CK(prim_box.alloc((size_t)ni * sizeof(PtBox))); PT_CK(bounds.alloc(32)); PT_CK(bp.alloc(sizeof(PtBuildParams)));
+        PT_CK(keys.alloc((size_t)ni * 8)); PT_CK(vals.alloc((size_t)ni * 4));
+        uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+        PT_CK(cudaMemcpyAsync(bounds.p, init, 24, cudaMemcpyHostToDevice, ctx->stream));
+        PT_LAUNCH(ctx, k_inst_boxes, grid_for(ctx, ni, 256, 8), 256, ctx->d_inst_in.as<PtInstance>(), ni, ctx->d_mesh_info.as<PtMeshInfo>(), prim_box.as<PtBox>(),
+                  bounds.as<uint32_t>());
+        PT_LAUNCH(ctx, k_build_params, 1, 32, bounds.as<uint32_t>(), bp.as<PtBuildParams>());
+        PT_LAUNCH(ctx, k_morton_boxes, grid_for(ctx, ni, 256, 8), 256, prim_box.as<PtBox>(), ni, bp.as<PtBuildParams>(), keys.as<uint64_t>(), vals.as<uint32_t>());
+        BuildOut out;
+        int32_t rc = build_bvh8(ctx, ni, prim_box.as<PtBox>(), keys, vals, bp.as<PtBuildParams>(), 1, &out);
+        if (rc) return rc;
+        sort_ms += out.sort_ms;
+        ctx->tlas_nodes = out.num_nodes;
+        uint32_t nb = out.num_nodes, tb = 0;
+        for (size_t k = 0; k < ctx->meshes.size(); ++k) { ctx->mesh_info[k].node_base = nb; ctx->mesh_info[k].tri_base = tb; nb += ctx->meshes[k].num_nodes; tb += ctx->meshes[k].ntris; }
+        PT_CK(cudaMemcpyAsync(ctx->d_mesh_info.p, ctx->mesh_info.data(), ctx->mesh_info.size() * sizeof(PtMeshInfo), cudaMemcpyHostToDevice, ctx->stream));
+        PT_CK(ctx->d_instances.alloc((size_t)ni * sizeof(PtInstance)));
+        PT_LAUNCH(ctx, k_write_instances, grid_for(ctx, ni, 256, 8), 256, ctx->d_inst_in.as<PtInstance>(), ni, out.order.as<uint32_t>(), out.leaf_seq.as<uint32_t>(),
+                  ctx->d_mesh_info.as<PtMeshInfo>(), ctx->d_instances.as<PtInstance>());
+        // flat arrays [TLAS | BLAS 0 | BLAS 1 ...]
+        PT_CK(ctx->d_nodes_all.alloc((size_t)nb * sizeof(PtNode8))); PT_CK(ctx->d_tris_all.alloc((size_t)tb * sizeof(PtTri)));
+        PT_CK(cudaMemcpyAsync(ctx->d_nodes_all.p, out.nodes.p, (size_t)out.num_nodes * sizeof(PtNode8), cudaMemcpyDeviceToDevice, ctx->stream));
+        for (size_t k = 0; k < ctx->meshes.size(); ++k) {
+            PT_CK(cudaMemcpyAsync(ctx->d_nodes_all.as<PtNode8>() + ctx->mesh_info[k].node_base, ctx->meshes[k].d_nodes.p, (size_t)ctx->meshes[k].num_nodes * sizeof(PtNode8),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+            PT_CK(cudaMemcpyAsync(ctx->d_tris_all.as<PtTri>() + ctx->mesh_info[k].tri_base, ctx->meshes[k].d_tris.p, (size_t)ctx->meshes[k].ntris * sizeof(PtTri),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        PtBuildParams hbp;
+        PT_CK(cudaMemcpyAsync(&hbp, bp.p, sizeof hbp, cudaMemcpyDeviceToHost, ctx->stream));
+        PT_CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(ctx->wlo, hbp.lo, 12); memcpy(ctx->whi, hbp.hi, 12);
+        ctx->d_tlas_order = std::move(out.order);
+        ctx->view.nodes = ctx->d_nodes_all.as<PtU4>(); ctx->view.tris = ctx->d_tris_all.as<PtU4>(); ctx->view.instances = ctx->d_instances.as<PtU4>();
+        total_nodes += out.num_nodes;
+    } else {
+        Mesh& m = ctx->meshes[0];
+        ctx->num_inst = 1; eff_tris = m.ntris; ctx->tlas_nodes = 0;
+        memcpy(ctx->wlo, m.lo, 12); memcpy(ctx->whi, m.hi, 12);
+        memcpy(ctx->mesh_info[0].lo, m.lo, 12); memcpy(ctx->mesh_info[0].hi, m.hi, 12);
+        ctx->mesh_info[0].pad = m.pad; ctx->mesh_info[0].ntris = m.ntris; ctx->mesh_info[0].nnodes = m.num_nodes;
+        ctx->d_nodes_all.release(); ctx->d_tris_all.release(); ctx->d_instances.release();
+        ctx->view.nodes = m.d_nodes.as<PtU4>(); ctx->view.tris = m.d_tris.as<PtU4>(); ctx->view.instances = nullptr;
+    }
+    // lights (host; emissive triangles are few) — instance order, then input triangle order
+    std::vector<PtLight> lights;
+    auto emissive = [&](uint32_t mid) -> const PtMaterial* {
+        const PtMaterial& mt = ctx->mats[mid < ctx->mats.size() ? mid : 0];
+        return (mt.er > 0 || mt.eg > 0 || mt.eb > 0) ? &mt : nullptr;
+    };
+    auto add_mesh_lights = [&](const Mesh& m, const float* o2w) {
+        for (uint32_t t = 0; t < m.ntris; ++t) {
+            const PtMaterial* mt = emissive(m.h_mat[t]);
+            if (!mt) continue;
+            float v[9]; m.host_tri(t, v);
+            pt_v3 v0 = pt_mk(v[0], v[1], v[2]), e1 = pt_mk(v[3] - v[0], v[4] - v[1], v[5] - v[2]), e2 = pt_mk(v[6] - v[0], v[7] - v[1], v[8] - v[2]);
+            if (o2w) { v0 = pt_xform_point(o2w, v0); e1 = pt_xform_vec(o2w, e1); e2 = pt_xform_vec(o2w, e2); }
+            PtLight l; pt_light_make(&l, v0, e1, e2, mt->er, mt->eg, mt->eb);
+            lights.push_back(l);
+        }
+    };
+    bool any_emissive = false;
+    for (auto& mt : ctx->mats) any_emissive |= (mt.er > 0 || mt.eg > 0 || mt.eb > 0);
+    if (any_emissive) {
+        if (ctx->two_level) for (uint32_t i = 0; i < ctx->num_inst; ++i) add_mesh_lights(ctx->meshes[rec[i].mesh_id], rec[i].o2w);
+        else add_mesh_lights(ctx->meshes[0], nullptr);
+    }
+    ctx->num_lights = (uint32_t)lights.size();
+    ctx->light_area = pt_lights_finalize(lights.data(), ctx->num_lights);
+    PT_CK(ctx->d_lights.alloc(lights.size() * sizeof(PtLight)));
+    if (!lights.empty()) PT_CK(cudaMemcpyAsync(ctx->d_lights.p, lights.data(), lights.size() * sizeof(PtLight), cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(ctx->d_mats.alloc(ctx->mats.size() * sizeof(PtMaterial)));
+    PT_CK(cudaMemcpyAsync(ctx->d_mats.p, ctx->mats.data(), ctx->mats.size() * sizeof(PtMaterial), cudaMemcpyHostToDevice, ctx->stream));
+    float ext = 0;
+    for (int k = 0; k < 3; ++k) ext = pt_max(ext, ctx->whi[k] - ctx->wlo[k]);
+    ctx->ray_eps = ext * PT_RAY_EPS_REL;
+    int32_t rc = ensure_status(ctx);
+    if (rc) return rc;
+    PT_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    foundation_pt_build_stats& bs = ctx->bstats;
+    bs.struct_size = sizeof bs; bs.num_meshes = (uint32_t)ctx->meshes.size(); bs.num_instances = ctx->num_inst; bs.num_triangles = total_tris;
+    bs.effective_triangles = eff_tris; bs.num_nodes8 = total_nodes; bs.device_bytes = total_nodes * sizeof(PtNode8) + total_tris * sizeof(PtTri);
+    bs.build_ms = ms; bs.sort_ms = sort_ms;
+    memcpy(bs.scene_lo, ctx->wlo, 12); memcpy(bs.scene_hi, ctx->whi, 12);
+    if (stats) *stats = bs;
+    ctx->stats.kernel_launches = ctx->call_launches; ctx->stats.last_ms = ms; ctx->stats.total_launches = ctx->total_launches;
+    ctx->committed = true;
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_camera_set(foundation_pt_context* ctx, const float view[16], const float proj[16]) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!view || !proj) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "camera_set: NULL matrix");
+    if (!pt_camera_derive(view, proj, &ctx->cam)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "camera_set: singular view/projection");
+    ctx->cam_set = true;
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_partition_set(foundation_pt_context* ctx, uint32_t rank, uint32_t count, uint32_t tile_size) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (count == 0 || rank >= count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "partition_set: rank must be < count");
+    ctx->part_rank = rank; ctx->part_count = count; ctx->part_tile = tile_size ? tile_size : 32;
+    ctx->wave_ready = false;
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_render(foundation_pt_context* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "render: scene not committed");
+    if (!ctx->cam_set) return ctx->fail(FOUNDATION_PT_ERR_STATE, "render: camera not set");
+    if (max_bounces > 64) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "render: max_bounces > 64");
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    int32_t rc = setup_wave(ctx);
+    if (rc) return rc;
+    begin_call(ctx);
+    if (sample_begin == 0) PT_CK(cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)ctx->cfg.width * ctx->cfg.height * 16, ctx->stream));
+    PT_CK(cudaMemsetAsync(ctx->w_ctr.p, 0, sizeof(PtWaveCounters), ctx->stream));
+    if (ctx->num_slots) {
+        rc = ctx->two_level ? render_impl<true>(ctx, sample_begin, sample_count, max_bounces) : render_impl<false>(ctx, sample_begin, sample_count, max_bounces);
+        if (rc) return rc;
+    }
+    rc = end_call(ctx);
+    if (rc) return rc;
+    PtWaveCounters c;
+    PT_CK(cudaMemcpy(&c, ctx->w_ctr.p, sizeof c, cudaMemcpyDeviceToHost));
+    ctx->stats.rays_extend = c.total_extend; ctx->stats.rays_shadow = c.total_shadow;
+    return check_status(ctx);
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_read_accum(foundation_pt_context* ctx, float* rgba, size_t size_bytes) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    size_t need = (size_t)ctx->cfg.width * ctx->cfg.height * 16;
+    if (!rgba || size_bytes < need) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "read_accum: buffer too small");
+    cudaSetDevice(ctx->device);
+    if (!ctx->d_accum.p) { memset(rgba, 0, need); return FOUNDATION_PT_OK; }
+    PT_CK(cudaMemcpyAsync(rgba, ctx->d_accum.p, need, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_resolve_rgba8(foundation_pt_context* ctx, uint8_t* rgba8, size_t size_bytes) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    uint32_t n = ctx->cfg.width * ctx->cfg.height;
+    if (!rgba8 || size_bytes < (size_t)n * 4) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "resolve_rgba8: buffer too small");
+    if (!ctx->d_accum.p) return ctx->fail(FOUNDATION_PT_ERR_STATE, "resolve_rgba8: nothing rendered");
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    DevBuf tmp; PT_CK(tmp.alloc((size_t)n * 4));
+    PT_LAUNCH(ctx, k_resolve_rgba8, grid_for(ctx, n, 256, 8), 256, ctx->d_accum.as<float4>(), n, tmp.as<uint32_t>());
+    PT_CK(cudaMemcpyAsync(rgba8, tmp.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_accum_device_ptr(foundation_pt_context* ctx, void** out_device_ptr, size_t* out_size_bytes) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!out_device_ptr) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "accum_device_ptr: NULL out pointer");
+    cudaSetDevice(ctx->device);
+    size_t need = (size_t)ctx->cfg.width * ctx->cfg.height * 16;
+    if (!ctx->d_accum.p) { PT_CK(ctx->d_accum.alloc(need)); PT_CK(cudaMemset(ctx->d_accum.p, 0, need)); }
+    *out_device_ptr = ctx->d_accum.p;
+    if (out_size_bytes) *out_size_bytes = need;
+    return FOUNDATION_PT_OK;
+}
+
+// ---- explicit ray sets --------------------------------------------------------------------------------
+int32_t foundation_pt_rays_upload(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!rays && count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "rays_upload: NULL rays");
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    if (ctx->d_rays.bytes < count * 32) {
+        PT_CK(ctx->d_rays.alloc(count * 32)); PT_CK(ctx->d_hits.alloc(count * 16)); PT_CK(ctx->d_hit_inst.alloc(count * 4)); PT_CK(ctx->d_occ.alloc(count));
+    }
+    ctx->num_rays = count;
+    if (count) PT_CK(cudaMemcpyAsync(ctx->d_rays.p, rays, count * 32, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+static int32_t rays_trace_common(foundation_pt_context* ctx, uint64_t first, uint64_t count, int mode) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "trace: scene not committed");
+    if (first + count > ctx->num_rays) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "trace: range exceeds the uploaded ray set");
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    begin_call(ctx);
+    const float4* rays = ctx->d_rays.as<float4>() + 2 * first;
+    int32_t rc = 0;
+    if (mode == 0) rc = launch_trace<false>(ctx, rays, count, ctx->d_hits.as<float4>() + first, ctx->d_hit_inst.as<uint32_t>() + first, nullptr);
+    else if (mode == 1) rc = launch_trace<true>(ctx, rays, count, nullptr, nullptr, ctx->d_occ.as<uint8_t>() + first);
+    else if (count) {
+        uint32_t grid = (uint32_t)((count + 127) / 128);
+        if (ctx->two_level)
+            PT_LAUNCH(ctx, k_trace_brute<true>, grid, 128, ctx->view, ctx->d_inst_in.as<PtInstance>(), ctx->num_inst, ctx->d_mesh_info.as<PtMeshInfo>(), 0u, rays,
+                      (unsigned long long)count, ctx->d_hits.as<float4>() + first, ctx->d_hit_inst.as<uint32_t>() + first);
+        else
+            PT_LAUNCH(ctx, k_trace_brute<false>, grid, 128, ctx->view, nullptr, 1u, nullptr, ctx->meshes[0].ntris, rays, (unsigned long long)count,
+                      ctx->d_hits.as<float4>() + first, ctx->d_hit_inst.as<uint32_t>() + first);
+        PT_CK(cudaGetLastError());
+    }
+    if (rc) return rc;
+    rc = end_call(ctx);
+    if (rc) return rc;
+    ctx->stats.trace_ms = ctx->stats.last_ms;
+    return check_status(ctx);
+    PT_CATCH(ctx)
+}
+int32_t foundation_pt_rays_trace_closest(foundation_pt_context* ctx, uint64_t first, uint64_t count) { return rays_trace_common(ctx, first, count, 0); }
+int32_t foundation_pt_rays_trace_any(foundation_pt_context* ctx, uint64_t first, uint64_t count) { return rays_trace_common(ctx, first, count, 1); }
+int32_t foundation_pt_rays_trace_brute(foundation_pt_context* ctx, uint64_t first, uint64_t count) { return rays_trace_common(ctx, first, count, 2); }
+
+int32_t foundation_pt_rays_download_hits(foundation_pt_context* ctx, uint64_t first, uint64_t count, foundation_pt_hit* out_hits, uint32_t* out_inst) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (first + count > ctx->num_rays) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "download_hits: range exceeds the uploaded ray set");
+    cudaSetDevice(ctx->device);
+    if (out_hits && count) PT_CK(cudaMemcpyAsync(out_hits, ctx->d_hits.as<float4>() + first, count * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_inst && count) PT_CK(cudaMemcpyAsync(out_inst, ctx->d_hit_inst.as<uint32_t>() + first, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return FOUNDATION_PT_OK;
+}
+
+// Host-buffer variants: H2D + kernel + D2H inside the call, chunked so copies of one chunk overlap the
+// traversal of another when the caller's buffers are pinned.
+int32_t foundation_pt_trace_closest(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count, foundation_pt_hit* out_hits, uint32_t* out_inst) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if ((!rays || !out_hits) && count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "trace_closest: NULL buffer");
+    if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "trace: scene not committed");
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    if (ctx->d_rays.bytes < count * 32) {
+        PT_CK(ctx->d_rays.alloc(count * 32)); PT_CK(ctx->d_hits.alloc(count * 16)); PT_CK(ctx->d_hit_inst.alloc(count * 4)); PT_CK(ctx->d_occ.alloc(count));
+    }
+    ctx->num_rays = count;
+    begin_call(ctx);
+    const uint64_t chunk = 1ull << 22;
+    cudaEvent_t done_h2d = ctx->ev2, done_k = ctx->ev3;
+    for (uint64_t b = 0; b < count; b += chunk) {
+        uint64_t n = count - b < chunk ? count - b : chunk;
+        PT_CK(cudaMemcpyAsync(ctx->d_rays.as<uint8_t>() + b * 32, rays + b, n * 32, cudaMemcpyHostToDevice, ctx->stream2));
+        PT_CK(cudaEventRecord(done_h2d, ctx->stream2));
+        PT_CK(cudaStreamWaitEvent(ctx->stream, done_h2d, 0));
+        int32_t rc = launch_trace<false>(ctx, ctx->d_rays.as<float4>() + 2 * b, n, ctx->d_hits.as<float4>() + b, ctx->d_hit_inst.as<uint32_t>() + b, nullptr);
+        if (rc) return rc;
+        PT_CK(cudaEventRecord(done_k, ctx->stream));
+        PT_CK(cudaStreamWaitEvent(ctx->stream2, done_k, 0));
+        PT_CK(cudaMemcpyAsync(out_hits + b, ctx->d_hits.as<float4>() + b, n * 16, cudaMemcpyDeviceToHost, ctx->stream2));
+        if (out_inst) PT_CK(cudaMemcpyAsync(out_inst + b, ctx->d_hit_inst.as<uint32_t>() + b, n * 4, cudaMemcpyDeviceToHost, ctx->stream2));
+    }
+    PT_CK(cudaStreamSynchronize(ctx->stream2));
+    int32_t rc = end_call(ctx);
+    if (rc) return rc;
+    return check_status(ctx);
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_trace_any(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count, uint8_t* out_occluded) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if ((!rays || !out_occluded) && count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "trace_any: NULL buffer");
+    int32_t rc = foundation_pt_rays_upload(ctx, rays, count);
+    if (rc) return rc;
+    rc = foundation_pt_rays_trace_any(ctx, 0, count);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    if (count) PT_CK(cudaMemcpy(out_occluded, ctx->d_occ.p, count, cudaMemcpyDeviceToHost));
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_stats_get(foundation_pt_context* ctx, foundation_pt_stats* stats) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!stats || stats->struct_size != sizeof(foundation_pt_stats)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "stats_get: NULL or struct_size mismatch");
+    ctx->stats.struct_size = sizeof(foundation_pt_stats);
+    ctx->stats.total_launches = ctx->total_launches;
+    *stats = ctx->stats;
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_blas_download(foundation_pt_context* ctx, uint32_t mesh_id, void* nodes, size_t nodes_bytes, void* tris, size_t tris_bytes, uint32_t* order,
+                                    size_t order_bytes, uint64_t* out_num_nodes, uint64_t* out_num_tris) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (mesh_id >= ctx->meshes.size()) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "blas_download: mesh_id out of range");
+    Mesh& m = ctx->meshes[mesh_id];
+    if (!m.d_nodes.p) return ctx->fail(FOUNDATION_PT_ERR_STATE, "blas_download: scene not committed");
+    cudaSetDevice(ctx->device);
+    if (out_num_nodes) *out_num_nodes = m.num_nodes;
+    if (out_num_tris) *out_num_tris = m.ntris;
+    if (nodes) { if (nodes_bytes < (size_t)m.num_nodes * 80) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "blas_download: nodes buffer too small"); PT_CK(cudaMemcpy(nodes, m.d_nodes.p, (size_t)m.num_nodes * 80, cudaMemcpyDeviceToHost)); }
+    if (tris) { if (tris_bytes < (size_t)m.ntris * 48) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "blas_download: tris buffer too small"); PT_CK(cudaMemcpy(tris, m.d_tris.p, (size_t)m.ntris * 48, cudaMemcpyDeviceToHost)); }
+    if (order) { if (order_bytes < (size_t)m.ntris * 4) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "blas_download: order buffer too small"); PT_CK(cudaMemcpy(order, m.d_order.p, (size_t)m.ntris * 4, cudaMemcpyDeviceToHost)); }
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_tlas_download(foundation_pt_context* ctx, void* nodes, size_t nodes_bytes, uint32_t* order, size_t order_bytes, uint64_t* out_num_nodes,
+                                    uint64_t* out_num_instances) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "tlas_download: scene not committed");
+    cudaSetDevice(ctx->device);
+    if (out_num_nodes) *out_num_nodes = ctx->tlas_nodes;
+    if (out_num_instances) *out_num_instances = ctx->two_level ? ctx->num_inst : 0;
+    if (!ctx->two_level) return FOUNDATION_PT_OK;
+    if (nodes) { if (nodes_bytes < (size_t)ctx->tlas_nodes * 80) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "tlas_download: nodes buffer too small"); PT_CK(cudaMemcpy(nodes, ctx->d_nodes_all.p, (size_t)ctx->tlas_nodes * 80, cudaMemcpyDeviceToHost)); }
+    if (order) { if (order_bytes < (size_t)ctx->num_inst * 4) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "tlas_download: order buffer too small"); PT_CK(cudaMemcpy(order, ctx->d_tlas_order.p, (size_t)ctx->num_inst * 4, cudaMemcpyDeviceToHost)); }
+    return FOUNDATION_PT_OK;
+}
+
+}  // extern "C"

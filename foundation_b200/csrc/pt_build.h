@@ -1,0 +1,147 @@
+// pt_build.h — per-work-item bodies of the acceleration-structure build (stages A1, A3, A5, A6 of
+// SURVEY.md §8a2): Morton keys, Karras-2012 LBVH emit, BVH2 -> BVH8 collapse with outward quantisation.
+// __host__ __device__ so the same bodies run inside the sm_100a kernels (pt_kernels.cuh) and inside the
+// CPU emulation harness used by the non-GPU tests; the cooperative parts (radix sort, scans, reductions,
+// atomics-ordered refit) live in pt_kernels.cuh only.
+// No reference counterpart: the reference builds no acceleration structure.
+#pragma once
+#include "pt_host_shared.h"
+#include "pt_layout.h"
+
+// Build-time BVH2 (n leaves in Morton order; n-1 internal nodes, root = 0).  A "ref" is an internal node
+// index (< n-1) or n-1 + sorted leaf position.  box[] is indexed by ref.
+struct PtBvh2 {
+    uint32_t n;
+    uint32_t *left, *right, *first, *last;  // n-1 each
+    uint32_t* parent;                       // 2n-1
+    PtBox* box;                             // 2n-1
+};
+
+PT_HD uint32_t pt_b2_count(const PtBvh2& b, uint32_t ref) { return ref < b.n - 1 ? b.last[ref] - b.first[ref] + 1 : 1u; }
+PT_HD uint32_t pt_b2_lopos(const PtBvh2& b, uint32_t ref) { return ref < b.n - 1 ? b.first[ref] : ref - (b.n - 1); }
+
+// ---- A1: Morton key of one primitive ----------------------------------------------------------------
+PT_HD pt_v3 pt_inv_extent(const float* lo, const float* hi) {
+    float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+    return pt_mk(ex > 0.0f ? pt_div(2097152.0f, ex) : 0.0f, ey > 0.0f ? pt_div(2097152.0f, ey) : 0.0f, ez > 0.0f ? pt_div(2097152.0f, ez) : 0.0f);
+}
+
+// ---- A3: one internal node of the radix tree (Karras 2012, index tie-break makes all keys distinct) ---
+PT_HD int pt_kdelta(const uint64_t* keys, uint32_t n, int64_t i, int64_t j) {
+    if (j < 0 || j >= (int64_t)n) return -1;
+    return pt_delta(keys[i], keys[j], (uint32_t)i, (uint32_t)j);
+}
+PT_HD void pt_karras_node(uint32_t idx, const uint64_t* keys, const PtBvh2& b) {
+    const uint32_t n = b.n;
+    const int64_t i = idx;
+    int64_t d = (pt_kdelta(keys, n, i, i + 1) - pt_kdelta(keys, n, i, i - 1)) > 0 ? 1 : -1;
+    int dmin = pt_kdelta(keys, n, i, i - d);
+    int64_t lmax = 2;
+    while (pt_kdelta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int64_t l = 0;
+    for (int64_t t = lmax / 2; t >= 1; t /= 2)
+        if (pt_kdelta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int64_t j = i + l * d;
+    int dnode = pt_kdelta(keys, n, i, j);
+    int64_t s = 0, t = l;
+    do {
+        t = (t + 1) / 2;
+        if (pt_kdelta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int64_t g = i + s * d + (d < 0 ? d : 0);
+    int64_t a = i < j ? i : j, e = i < j ? j : i;
+    uint32_t L = (a == g) ? (uint32_t)(n - 1 + g) : (uint32_t)g;
+    uint32_t R = (e == g + 1) ? (uint32_t)(n - 1 + g + 1) : (uint32_t)(g + 1);
+    b.left[idx] = L; b.right[idx] = R; b.first[idx] = (uint32_t)a; b.last[idx] = (uint32_t)e;
+    b.parent[L] = idx; b.parent[R] = idx;
+}
+
+// ---- A5 phase 1: choose up to 8 children of one wide node and give them octant slots -------------------
+// ref: BVH2 ref the wide node stands for.  slot_ref[s] = child ref or PT_NONE.
+PT_HD void pt_collapse_select(const PtBvh2& b, uint32_t ref, uint32_t max_leaf, uint32_t* slot_ref, uint32_t* n_internal, uint32_t* n_prims) {
+    uint32_t C[8];
+    int nc = 0;
+    if (pt_b2_count(b, ref) <= max_leaf) C[nc++] = ref;
+    else {
+        C[nc++] = b.left[ref]; C[nc++] = b.right[ref];
+        while (nc < 8) {
+            int best = -1; float best_area = 0.0f;
+            for (int k = 0; k < nc; ++k) {
+                if (pt_b2_count(b, C[k]) <= max_leaf) continue;
+                const PtBox x = b.box[C[k]];
+                float ar = pt_box_area(x.lox, x.loy, x.loz, x.hix, x.hiy, x.hiz);
+                if (best < 0 || ar > best_area) { best_area = ar; best = k; }
+            }
+            if (best < 0) break;
+            uint32_t r = C[best];
+            C[best] = b.left[r]; C[nc++] = b.right[r];
+        }
+    }
+    const PtBox nb = b.box[ref];
+    float cx = (nb.lox + nb.hix) * 0.5f, cy = (nb.loy + nb.hiy) * 0.5f, cz = (nb.loz + nb.hiz) * 0.5f;
+    float dx[8], dy[8], dz[8];
+    for (int k = 0; k < nc; ++k) {
+        const PtBox cb = b.box[C[k]];
+        dx[k] = (cb.lox + cb.hix) * 0.5f - cx; dy[k] = (cb.loy + cb.hiy) * 0.5f - cy; dz[k] = (cb.loz + cb.hiz) * 0.5f - cz;
+    }
+    uint32_t child_done = 0, slot_used = 0;
+    for (int s = 0; s < 8; ++s) slot_ref[s] = PT_NONE;
+    for (int it = 0; it < nc; ++it) {
+        int bk = -1, bs = -1; float bc = 0.0f;
+        for (int k = 0; k < nc; ++k) {
+            if (child_done >> k & 1u) continue;
+            for (int s = 0; s < 8; ++s) {
+                if (slot_used >> s & 1u) continue;
+                float c = (((s & 4) ? dx[k] : -dx[k]) + ((s & 2) ? dy[k] : -dy[k])) + ((s & 1) ? dz[k] : -dz[k]);
+                if (bk < 0 || c > bc) { bc = c; bk = k; bs = s; }
+            }
+        }
+        slot_ref[bs] = C[bk]; child_done |= 1u << bk; slot_used |= 1u << bs;
+    }
+    uint32_t ni = 0, np = 0;
+    for (int s = 0; s < 8; ++s) {
+        if (slot_ref[s] == PT_NONE) continue;
+        uint32_t cnt = pt_b2_count(b, slot_ref[s]);
+        if (cnt <= max_leaf) np += cnt; else ni += 1;
+    }
+    *n_internal = ni; *n_prims = np;
+}
+
+// ---- A5 phase 2: write the 80-byte node, the next level's refs and the leaf sequence ---------------------
+PT_HD void pt_collapse_emit(const PtBvh2& b, uint32_t ref, const uint32_t* slot_ref, uint32_t max_leaf, float pad, uint32_t child_base,
+                            uint32_t prim_base, PtNode8* out, uint32_t* next_refs /* at this node's first child */, uint32_t* leaf_seq /* global */) {
+    const PtBox nb = b.box[ref];
+    PtNode8 nd;
+    float p[3] = {nb.lox - pad, nb.loy - pad, nb.loz - pad};
+    float hi[3] = {nb.hix + pad, nb.hiy + pad, nb.hiz + pad};
+    float inv[3]; uint32_t e[3];
+    for (int k = 0; k < 3; ++k) { e[k] = pt_quant_exp(hi[k] - p[k]); inv[k] = pt_u2f((254u - e[k]) << 23); }
+    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
+    nd.ex = (uint8_t)e[0]; nd.ey = (uint8_t)e[1]; nd.ez = (uint8_t)e[2]; nd.imask = 0;
+    nd.child_base = child_base; nd.tri_base = prim_base;
+    uint32_t off = 0, nint = 0;
+    for (int s = 0; s < 8; ++s) {
+        uint32_t r = slot_ref[s];
+        if (r == PT_NONE) {
+            nd.meta[s] = 0;
+            nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255; nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
+            continue;
+        }
+        const PtBox cb = b.box[r];
+        nd.qlox[s] = (uint8_t)pt_quant_lo(cb.lox - pad, p[0], inv[0]); nd.qhix[s] = (uint8_t)pt_quant_hi(cb.hix + pad, p[0], inv[0]);
+        nd.qloy[s] = (uint8_t)pt_quant_lo(cb.loy - pad, p[1], inv[1]); nd.qhiy[s] = (uint8_t)pt_quant_hi(cb.hiy + pad, p[1], inv[1]);
+        nd.qloz[s] = (uint8_t)pt_quant_lo(cb.loz - pad, p[2], inv[2]); nd.qhiz[s] = (uint8_t)pt_quant_hi(cb.hiz + pad, p[2], inv[2]);
+        uint32_t cnt = pt_b2_count(b, r);
+        if (cnt <= max_leaf) {
+            uint32_t fp = pt_b2_lopos(b, r);
+            nd.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | off);
+            for (uint32_t q = 0; q < cnt; ++q) leaf_seq[prim_base + off + q] = fp + q;
+            off += cnt;
+        } else {
+            nd.imask |= (uint8_t)(1u << s);
+            nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
+            next_refs[nint++] = r;
+        }
+    }
+    *out = nd;
+}

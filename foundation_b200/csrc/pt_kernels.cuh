@@ -1,0 +1,637 @@
+// pt_kernels.cuh — every sm_100a kernel of the path-tracing hot path.
+// Hand-written CUDA; no CUB/Thrust, no OptiX, no tensor cores (nothing here is a dense contraction).
+// Compiled with --fmad=false: fused multiply-adds happen exactly where pt_math.h says pt_fma.
+// The reference has no counterpart for any kernel in this file (it launches no compute work at all:
+// src/Platform/RHI/Command.hpp:38-115 has no Dispatch); the per-item arithmetic is in the shared headers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pt_build.h"
+#include "pt_shading.h"
+#include "pt_traverse.h"
+
+#define PT_FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------------
+// small device utilities
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pt_f2ord(float f) {  // order-preserving float -> uint map for atomicMin/Max
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float pt_ord2f(uint32_t u) {
+    uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(v);
+#else
+    float f; memcpy(&f, &v, 4); return f;
+#endif
+}
+__device__ __forceinline__ PtU4 pt_ldg4(const PtU4* p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    PtU4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+}
+__device__ __forceinline__ uint32_t pt_lane() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t pt_gtid() { return blockIdx.x * blockDim.x + threadIdx.x; }
+__device__ __forceinline__ uint32_t pt_gsize() { return gridDim.x * blockDim.x; }
+
+// ---------------------------------------------------------------------------------------------------
+// raw mesh access: positions with byte stride, u16 / u32 / no indices (formats of RHIResourceFormat,
+// mos9527/Foundation src/Platform/RHI/Common.hpp:18-27)
+// ---------------------------------------------------------------------------------------------------
+struct PtMeshRaw {
+    const uint8_t* pos; uint32_t stride; const void* idx; uint32_t idx_fmt; uint32_t ntris; const uint32_t* mat;
+};
+__device__ __forceinline__ pt_v3 pt_load_vertex(const PtMeshRaw& m, uint32_t v) {
+    const float* p = reinterpret_cast<const float*>(m.pos + (size_t)v * m.stride);
+    return pt_mk(p[0], p[1], p[2]);
+}
+__device__ __forceinline__ void pt_load_tri(const PtMeshRaw& m, uint32_t i, pt_v3* a, pt_v3* b, pt_v3* c) {
+    uint32_t i0, i1, i2;
+    if (m.idx_fmt == 32) { const uint32_t* q = (const uint32_t*)m.idx + 3 * (size_t)i; i0 = q[0]; i1 = q[1]; i2 = q[2]; }
+    else if (m.idx_fmt == 16) { const uint16_t* q = (const uint16_t*)m.idx + 3 * (size_t)i; i0 = q[0]; i1 = q[1]; i2 = q[2]; }
+    else { i0 = 3 * i; i1 = i0 + 1; i2 = i0 + 2; }
+    *a = pt_load_vertex(m, i0); *b = pt_load_vertex(m, i1); *c = pt_load_vertex(m, i2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A1: primitive boxes + scene bounds (warp-shuffle reduce, one ordered-uint atomic per warp and plane)
+// bounds[0..2] = lo (init 0xffffffff), bounds[3..5] = hi (init 0)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pt_reduce_bounds(PtBox bx, bool valid, uint32_t* bounds) {
+    uint32_t lo[3] = {valid ? pt_f2ord(bx.lox) : 0xffffffffu, valid ? pt_f2ord(bx.loy) : 0xffffffffu, valid ? pt_f2ord(bx.loz) : 0xffffffffu};
+    uint32_t hi[3] = {valid ? pt_f2ord(bx.hix) : 0u, valid ? pt_f2ord(bx.hiy) : 0u, valid ? pt_f2ord(bx.hiz) : 0u};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = __reduce_min_sync(PT_FULL, lo[k]);
+        hi[k] = __reduce_max_sync(PT_FULL, hi[k]);
+    }
+    if (pt_lane() == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(&bounds[k], lo[k]); atomicMax(&bounds[3 + k], hi[k]); }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tri_boxes(PtMeshRaw m, PtBox* prim_box, uint32_t* bounds) {
+    uint32_t n = m.ntris;
+    uint32_t rounds = (n + pt_gsize() - 1) / pt_gsize();
+    for (uint32_t r = 0; r < rounds; ++r) {   // uniform trip count: the warp reduce needs all lanes
+        uint32_t i = r * pt_gsize() + pt_gtid();
+        bool valid = i < n;
+        PtBox bx = {0, 0, 0, 0, 0, 0};
+        if (valid) {
+            pt_v3 a, b, c;
+            pt_load_tri(m, i, &a, &b, &c);
+            bx.lox = pt_min(pt_min(a.x, b.x), c.x); bx.loy = pt_min(pt_min(a.y, b.y), c.y); bx.loz = pt_min(pt_min(a.z, b.z), c.z);
+            bx.hix = pt_max(pt_max(a.x, b.x), c.x); bx.hiy = pt_max(pt_max(a.y, b.y), c.y); bx.hiz = pt_max(pt_max(a.z, b.z), c.z);
+            prim_box[i] = bx;
+        }
+        pt_reduce_bounds(bx, valid, bounds);
+    }
+}
+
+// device-resident build parameters derived from the reduced bounds (no host round trip)
+struct PtBuildParams { float lo[3], hi[3]; float pad; float inv[3]; };
+__global__ void k_build_params(const uint32_t* bounds, PtBuildParams* bp) {
+    if (pt_gtid() != 0) return;
+    for (int k = 0; k < 3; ++k) { bp->lo[k] = pt_ord2f(bounds[k]); bp->hi[k] = pt_ord2f(bounds[3 + k]); }
+    bp->pad = pt_pad_for(bp->lo, bp->hi);
+    pt_v3 inv = pt_inv_extent(bp->lo, bp->hi);
+    bp->inv[0] = inv.x; bp->inv[1] = inv.y; bp->inv[2] = inv.z;
+}
+
+__global__ void __launch_bounds__(256) k_morton_tris(PtMeshRaw m, const PtBuildParams* bp, uint64_t* keys, uint32_t* vals) {
+    pt_v3 lo = pt_mk(bp->lo[0], bp->lo[1], bp->lo[2]), inv = pt_mk(bp->inv[0], bp->inv[1], bp->inv[2]);
+    for (uint32_t i = pt_gtid(); i < m.ntris; i += pt_gsize()) {
+        pt_v3 a, b, c;
+        pt_load_tri(m, i, &a, &b, &c);
+        keys[i] = pt_morton63(pt_tri_centroid(a, b, c), lo, inv);
+        vals[i] = i;
+    }
+}
+__global__ void __launch_bounds__(256) k_morton_boxes(const PtBox* prim_box, uint32_t n, const PtBuildParams* bp, uint64_t* keys, uint32_t* vals) {
+    pt_v3 lo = pt_mk(bp->lo[0], bp->lo[1], bp->lo[2]), inv = pt_mk(bp->inv[0], bp->inv[1], bp->inv[2]);
+    for (uint32_t i = pt_gtid(); i < n; i += pt_gsize()) {
+        PtBox b = prim_box[i];
+        pt_v3 c = pt_mk((b.lox + b.hix) * 0.5f, (b.loy + b.hiy) * 0.5f, (b.loz + b.hiz) * 0.5f);
+        keys[i] = pt_morton63(c, lo, inv);
+        vals[i] = i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exclusive scan of uint32 (two levels: 4096-element chunks, then one block over the chunk sums)
+// ---------------------------------------------------------------------------------------------------
+#define PT_SCAN_THREADS 256
+#define PT_SCAN_ITEMS 16
+#define PT_SCAN_CHUNK (PT_SCAN_THREADS * PT_SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t pt_block_excl_scan(uint32_t v, uint32_t* total) {  // blockDim.x multiple of 32, <= 1024
+    __shared__ uint32_t warp_sums[33];
+    const uint32_t lane = pt_lane(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(PT_FULL, inc, o); if (lane >= (uint32_t)o) inc += t; }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nwarps ? warp_sums[lane] : 0u, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(PT_FULL, wi, o); if (lane >= (uint32_t)o) wi += t; }
+        warp_sums[lane] = wi - w;             // exclusive prefix of the warp sums
+        if (lane == 31) warp_sums[32] = wi;   // block total
+    }
+    __syncthreads();
+    uint32_t res = warp_sums[warp] + inc - v;
+    *total = warp_sums[32];
+    __syncthreads();                          // warp_sums is reused by the next call
+    return res;
+}
+
+__global__ void __launch_bounds__(PT_SCAN_THREADS) k_scan_chunks(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* chunk_sums) {
+    uint32_t base = blockIdx.x * PT_SCAN_CHUNK + threadIdx.x * PT_SCAN_ITEMS;
+    uint32_t v[PT_SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PT_SCAN_ITEMS; ++k) { uint32_t i = base + k; v[k] = i < n ? in[i] : 0; sum += v[k]; }
+    uint32_t total;
+    uint32_t excl = pt_block_excl_scan(sum, &total);
+#pragma unroll
+    for (int k = 0; k < PT_SCAN_ITEMS; ++k) { uint32_t i = base + k; if (i < n) out[i] = excl; excl += v[k]; }
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
+}
+// one block; scans m chunk sums in place (exclusive) and writes the grand total
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, uint32_t m, uint32_t* grand_total) {
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < m; b += 1024) {
+        uint32_t i = b + threadIdx.x;
+        uint32_t v = i < m ? sums[i] : 0, total;
+        uint32_t e = pt_block_excl_scan(v, &total);
+        if (i < m) sums[i] = carry + e;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && grand_total) *grand_total = carry;
+}
+__global__ void __launch_bounds__(PT_SCAN_THREADS) k_scan_add(uint32_t* out, uint32_t n, const uint32_t* chunk_sums) {
+    uint32_t add = chunk_sums[blockIdx.x];
+    uint32_t base = blockIdx.x * PT_SCAN_CHUNK;
+    for (uint32_t k = threadIdx.x; k < PT_SCAN_CHUNK; k += PT_SCAN_THREADS) { uint32_t i = base + k; if (i < n) out[i] += add; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A2: stable LSD radix sort of (uint64 key, uint32 value), 8 bits per pass.
+// Per pass: per-tile digit histogram -> exclusive scan over [digit][tile] -> stable scatter.  Stability
+// inside a tile: rounds in order, warps in order (shared prefix over per-warp digit counts), lanes in order
+// (match_any + popc of lower lanes).
+// ---------------------------------------------------------------------------------------------------
+#define PT_RS_THREADS 256
+#define PT_RS_ROUNDS 16
+#define PT_RS_TILE (PT_RS_THREADS * PT_RS_ROUNDS)
+
+__global__ void __launch_bounds__(PT_RS_THREADS) k_rs_hist(const uint64_t* keys, uint32_t n, int shift, uint32_t* tile_hist, uint32_t num_tiles) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * PT_RS_TILE;
+#pragma unroll 4
+    for (int r = 0; r < PT_RS_ROUNDS; ++r) {
+        uint32_t i = base + r * PT_RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    tile_hist[threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(PT_RS_THREADS) k_rs_scatter(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout, uint32_t n,
+                                                              int shift, const uint32_t* tile_off, uint32_t num_tiles) {
+    __shared__ uint32_t wcnt[PT_RS_THREADS / 32][256];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t run = tile_off[tid * num_tiles + blockIdx.x];   // next output position of digit `tid` for this tile
+    const uint32_t base = blockIdx.x * PT_RS_TILE;
+    for (int r = 0; r < PT_RS_ROUNDS; ++r) {
+        uint32_t i = base + r * PT_RS_THREADS + tid;
+        bool valid = i < n;
+        uint64_t key = valid ? kin[i] : 0ull;
+        uint32_t val = valid ? vin[i] : 0u;
+        uint32_t dig = valid ? ((uint32_t)(key >> shift) & 255u) : (0x10000u + lane);
+#pragma unroll
+        for (int w = 0; w < PT_RS_THREADS / 32; ++w) wcnt[w][tid] = 0;
+        __syncthreads();
+        uint32_t peers = __match_any_sync(PT_FULL, dig);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) wcnt[warp][dig] = __popc(peers);
+        __syncthreads();
+        uint32_t acc = run;
+#pragma unroll
+        for (int w = 0; w < PT_RS_THREADS / 32; ++w) { uint32_t c = wcnt[w][tid]; wcnt[w][tid] = acc; acc += c; }
+        run = acc;
+        __syncthreads();
+        if (valid) { uint32_t pos = wcnt[warp][dig] + rank; kout[pos] = key; vout[pos] = val; }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A3 / A4: Karras emit and bottom-up refit (second arriver proceeds)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_karras(const uint64_t* keys, PtBvh2 b) {
+    for (uint32_t i = pt_gtid(); i + 1 < b.n; i += pt_gsize()) pt_karras_node(i, keys, b);
+}
+__device__ __forceinline__ PtBox pt_ldcg_box(const PtBox* p) {
+    const float* f = reinterpret_cast<const float*>(p);
+    PtBox b; b.lox = __ldcg(f); b.loy = __ldcg(f + 1); b.loz = __ldcg(f + 2); b.hix = __ldcg(f + 3); b.hiy = __ldcg(f + 4); b.hiz = __ldcg(f + 5);
+    return b;
+}
+__global__ void __launch_bounds__(256) k_refit(PtBvh2 b, const PtBox* prim_box, const uint32_t* order, uint32_t* flags) {
+    const uint32_t n = b.n;
+    for (uint32_t j = pt_gtid(); j < n; j += pt_gsize()) {
+        b.box[n - 1 + j] = prim_box[order[j]];
+        if (n == 1) return;
+        uint32_t cur = b.parent[n - 1 + j];
+        for (;;) {
+            __threadfence();
+            if (atomicAdd(&flags[cur], 1u) == 0u) break;
+            PtBox l = pt_ldcg_box(&b.box[b.left[cur]]), r = pt_ldcg_box(&b.box[b.right[cur]]);
+            PtBox u;
+            u.lox = pt_min(l.lox, r.lox); u.loy = pt_min(l.loy, r.loy); u.loz = pt_min(l.loz, r.loz);
+            u.hix = pt_max(l.hix, r.hix); u.hiy = pt_max(l.hiy, r.hiy); u.hiz = pt_max(l.hiz, r.hiz);
+            b.box[cur] = u;
+            if (cur == 0) break;
+            cur = b.parent[cur];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A5: level-synchronous BVH2 -> BVH8 collapse
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_collapse_select(PtBvh2 b, const uint32_t* refs, uint32_t m, uint32_t max_leaf, uint32_t* slots, uint32_t* n_int,
+                                                         uint32_t* n_prim) {
+    for (uint32_t w = pt_gtid(); w < m; w += pt_gsize()) {
+        uint32_t s[8], ni, np;
+        pt_collapse_select(b, refs[w], max_leaf, s, &ni, &np);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) slots[8 * (size_t)w + k] = s[k];
+        n_int[w] = ni; n_prim[w] = np;
+    }
+}
+__global__ void __launch_bounds__(128) k_collapse_emit(PtBvh2 b, const uint32_t* refs, uint32_t m, uint32_t max_leaf, const PtBuildParams* bp,
+                                                       const uint32_t* slots, const uint32_t* off_int, const uint32_t* off_prim, uint32_t level_start,
+                                                       uint32_t next_start, uint32_t prim_total, PtNode8* nodes, uint32_t* next_refs, uint32_t* leaf_seq) {
+    const float pad = bp->pad;
+    for (uint32_t w = pt_gtid(); w < m; w += pt_gsize()) {
+        uint32_t s[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = slots[8 * (size_t)w + k];
+        pt_collapse_emit(b, refs[w], s, max_leaf, pad, next_start + off_int[w], prim_total + off_prim[w], &nodes[level_start + w], next_refs + off_int[w],
+                         leaf_seq);
+    }
+}
+__global__ void __launch_bounds__(256) k_write_tris(PtMeshRaw m, const uint32_t* order, const uint32_t* leaf_seq, PtTri* tris) {
+    for (uint32_t k = pt_gtid(); k < m.ntris; k += pt_gsize()) {
+        uint32_t i = order[leaf_seq[k]];
+        pt_v3 a, b, c;
+        pt_load_tri(m, i, &a, &b, &c);
+        PtTri t;
+        t.v0x = a.x; t.v0y = a.y; t.v0z = a.z; t.prim = i;
+        t.e1x = b.x - a.x; t.e1y = b.y - a.y; t.e1z = b.z - a.z; t.mat = m.mat ? m.mat[i] : 0u;
+        t.e2x = c.x - a.x; t.e2y = c.y - a.y; t.e2z = c.z - a.z; t.pad = 0u;
+        uint4* dst = reinterpret_cast<uint4*>(tris + k);
+        const uint4* src = reinterpret_cast<const uint4*>(&t);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A6: TLAS inputs — world boxes of instances, and the leaf-ordered instance records
+// ---------------------------------------------------------------------------------------------------
+struct PtMeshInfo { float lo[3], hi[3]; float pad; uint32_t node_base, tri_base, ntris, nnodes; };
+__global__ void __launch_bounds__(256) k_inst_boxes(const PtInstance* inst, uint32_t n, const PtMeshInfo* meshes, PtBox* prim_box, uint32_t* bounds) {
+    uint32_t rounds = (n + pt_gsize() - 1) / pt_gsize();
+    for (uint32_t r = 0; r < rounds; ++r) {
+        uint32_t i = r * pt_gsize() + pt_gtid();
+        bool valid = i < n;
+        PtBox bx = {0, 0, 0, 0, 0, 0};
+        if (valid) {
+            const PtMeshInfo mi = meshes[inst[i].mesh_id];
+            float lo[3], hi[3], wlo[3], whi[3], o2w[12];
+            for (int k = 0; k < 3; ++k) { lo[k] = mi.lo[k] - mi.pad; hi[k] = mi.hi[k] + mi.pad; }
+            for (int k = 0; k < 12; ++k) o2w[k] = inst[i].o2w[k];
+            pt_world_box(o2w, lo, hi, wlo, whi);
+            bx.lox = wlo[0]; bx.loy = wlo[1]; bx.loz = wlo[2]; bx.hix = whi[0]; bx.hiy = whi[1]; bx.hiz = whi[2];
+            prim_box[i] = bx;
+        }
+        pt_reduce_bounds(bx, valid, bounds);
+    }
+}
+__global__ void __launch_bounds__(256) k_write_instances(const PtInstance* in, uint32_t n, const uint32_t* order, const uint32_t* leaf_seq,
+                                                         const PtMeshInfo* meshes, PtInstance* out) {
+    for (uint32_t k = pt_gtid(); k < n; k += pt_gsize()) {
+        PtInstance r = in[order[leaf_seq[k]]];
+        r.node_base = meshes[r.mesh_id].node_base; r.tri_base = meshes[r.mesh_id].tri_base;
+        out[k] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// B2 / B5 on explicit ray sets: closest-hit and any-hit kernels (one lane per ray, 128-bit coalesced
+// loads of the 32-byte ray records, 128-bit stores of the 16-byte hit records)
+// ---------------------------------------------------------------------------------------------------
+struct PtDevCounters { unsigned long long nodes, tris, insts; };
+
+template <bool ANY, bool TWO_LEVEL, bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_rays(PtSceneView sc, const float4* __restrict__ rays, unsigned long long n, float4* __restrict__ hits,
+                                                    uint32_t* __restrict__ inst_out, uint8_t* __restrict__ occ, uint32_t* status, PtDevCounters* counters) {
+    PtCount cnt; cnt.nodes = cnt.tris = cnt.insts = 0;
+    PtNoCount nocnt;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+        PtHitRec h;
+        bool ok;
+        if (COUNT) ok = pt_traverse<ANY, TWO_LEVEL>(sc, pt_mk(a.x, a.y, a.z), pt_mk(b.x, b.y, b.z), a.w, b.w, &h, cnt);
+        else ok = pt_traverse<ANY, TWO_LEVEL>(sc, pt_mk(a.x, a.y, a.z), pt_mk(b.x, b.y, b.z), a.w, b.w, &h, nocnt);
+        if (!ok) atomicOr(status, 1u);
+        if (ANY) occ[i] = h.prim != PT_NONE ? 1 : 0;
+        else {
+            float4 o;
+            if (h.prim == PT_NONE) { o.x = __uint_as_float(PT_INF_BITS); o.y = 0.0f; o.z = 0.0f; }
+            else { o.x = h.t; o.y = pt_div(h.U, h.ad); o.z = pt_div(h.V, h.ad); }
+            o.w = __uint_as_float(h.prim);
+            hits[i] = o;
+            if (inst_out) inst_out[i] = h.inst;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&counters->nodes, (unsigned long long)cnt.nodes); atomicAdd(&counters->tris, (unsigned long long)cnt.tris);
+        atomicAdd(&counters->insts, (unsigned long long)cnt.insts);
+    }
+}
+
+// Exhaustive closest hit: every triangle of every instance, no BVH (device-side ground truth for tests).
+// One lane per ray; all lanes of a block read the same triangle (broadcast), staged through shared memory.
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(128) k_trace_brute(PtSceneView sc, const PtInstance* inst_in, uint32_t num_inst, const PtMeshInfo* meshes,
+                                                     uint32_t flat_ntris, const float4* __restrict__ rays, unsigned long long n, float4* __restrict__ hits,
+                                                     uint32_t* __restrict__ inst_out) {
+    __shared__ PtU4 tile[3 * 128];
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < n;
+    float4 a = valid ? rays[2 * i] : make_float4(0, 0, 0, 0), b = valid ? rays[2 * i + 1] : make_float4(0, 0, 0, 0);
+    PtHitRec best; best.t = b.w; best.U = best.V = 0; best.ad = 1; best.prim = PT_NONE; best.inst = PT_NONE; best.tidx = best.iidx = 0;
+    PtNoCount nc;
+    uint32_t ninst = TWO_LEVEL ? num_inst : 1u;
+    for (uint32_t ii = 0; ii < ninst; ++ii) {
+        PtRayCtx r;
+        uint32_t tri_base = 0, ntris = flat_ntris, inst_id = 0;
+        if (TWO_LEVEL) {
+            float w2o[12];
+            for (int k = 0; k < 12; ++k) w2o[k] = inst_in[ii].w2o[k];
+            pt_ray_ctx(&r, pt_xform_point(w2o, pt_mk(a.x, a.y, a.z)), pt_xform_vec(w2o, pt_mk(b.x, b.y, b.z)));
+            tri_base = meshes[inst_in[ii].mesh_id].tri_base; ntris = meshes[inst_in[ii].mesh_id].ntris; inst_id = inst_in[ii].inst_id;
+        } else pt_ray_ctx(&r, pt_mk(a.x, a.y, a.z), pt_mk(b.x, b.y, b.z));
+        for (uint32_t t0 = 0; t0 < ntris; t0 += 128) {
+            __syncthreads();
+            uint32_t cntt = min(128u, ntris - t0);
+            for (uint32_t k = threadIdx.x; k < 3 * cntt; k += blockDim.x) tile[k] = sc.tris[3 * (size_t)(tri_base + t0) + k];
+            __syncthreads();
+            if (valid)
+                for (uint32_t k = 0; k < cntt; ++k) pt_test_tri(tile, k, r, a.w, inst_id, ii, &best, nc);
+        }
+    }
+    if (!valid) return;
+    float4 o;
+    if (best.prim == PT_NONE) { o.x = __uint_as_float(PT_INF_BITS); o.y = 0.0f; o.z = 0.0f; }
+    else { o.x = best.t; o.y = pt_div(best.U, best.ad); o.z = pt_div(best.V, best.ad); }
+    o.w = __uint_as_float(best.prim);
+    hits[i] = o;
+    if (inst_out) inst_out[i] = best.inst;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Wavefront path tracer state (SoA, one float4 / uint4 array per field; slot = one owned pixel)
+// ---------------------------------------------------------------------------------------------------
+struct PtWaveCounters {
+    uint32_t n_active, n_next, n_shadow, pad;
+    unsigned long long total_extend, total_shadow;
+};
+struct PtWave {
+    float4* ray_o;     // o.xyz, pdf_prev
+    float4* ray_d;     // d.xyz, bounce (uint bits)
+    float4* beta;      // beta.rgb, pixel (uint bits)
+    float4* L;         // L.rgb, unused
+    uint4* rng;        // state lo/hi, inc lo/hi
+    float4* hit;       // t, tidx (bits), iidx (bits), sort key (bits)
+    uint32_t* active;  // slots alive this bounce
+    uint32_t* next;    // slots alive next bounce
+    uint32_t* sorted;  // active, reordered by material key
+    float4* sh_o;      // shadow ray o.xyz, tmax
+    float4* sh_d;      // shadow ray d.xyz, slot (bits)
+    float4* sh_c;      // contribution rgb
+    const uint32_t* slot_pixel;   // slot -> pixel index (tile partition), or nullptr = identity
+    PtWaveCounters* ctr;
+    uint32_t* key_hist;           // PT_KEY_BUCKETS + 1 counters for the material sort
+    uint32_t num_slots;
+};
+#define PT_KEY_BUCKETS 1024u      // material ids >= 1023 share the last bucket; bucket 1023+1 = miss
+#define PT_KEY_MISS PT_KEY_BUCKETS
+
+struct PtFrame {
+    PtCamera cam; uint64_t seed; uint32_t width, height, sample;
+};
+
+// B1: ray generation (one lane per slot)
+__global__ void __launch_bounds__(256) k_raygen(PtWave w, PtFrame f) {
+    for (uint32_t s = pt_gtid(); s < w.num_slots; s += pt_gsize()) {
+        uint32_t pixel = w.slot_pixel ? w.slot_pixel[s] : s;
+        PtPath p;
+        pt_path_init(&p, f.cam, f.seed, pixel, f.sample, f.width, f.height);
+        w.ray_o[s] = make_float4(p.o.x, p.o.y, p.o.z, 0.0f);
+        w.ray_d[s] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(0u));
+        w.beta[s] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel));
+        w.L[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        w.rng[s] = make_uint4((uint32_t)p.rng.state, (uint32_t)(p.rng.state >> 32), (uint32_t)p.rng.inc, (uint32_t)(p.rng.inc >> 32));
+        w.active[s] = s;
+    }
+    if (pt_gtid() == 0) { w.ctr->n_active = w.num_slots; w.ctr->n_next = 0; w.ctr->n_shadow = 0; }
+}
+
+// B2: extend — closest hit for every active path; also emits the material sort key and its histogram
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(128) k_extend(PtSceneView sc, PtWave w, uint32_t* status, int do_hist) {
+    const uint32_t n = w.ctr->n_active;
+    const uint32_t rounds = (n + pt_gsize() - 1) / pt_gsize();
+    PtNoCount nc;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        uint32_t j = r * pt_gsize() + pt_gtid();
+        bool valid = j < n;
+        uint32_t key = 0xffff0000u + pt_lane();   // invalid lanes: unique keys, never counted
+        if (valid) {
+            uint32_t s = w.active[j];
+            float4 o = w.ray_o[s], d = w.ray_d[s];
+            PtHitRec h;
+            if (!pt_traverse<false, TWO_LEVEL>(sc, pt_mk(o.x, o.y, o.z), pt_mk(d.x, d.y, d.z), 0.0f, __uint_as_float(PT_INF_BITS), &h, nc)) atomicOr(status, 1u);
+            key = PT_KEY_MISS;
+            if (h.prim != PT_NONE) {
+                uint32_t mat = __ldg(reinterpret_cast<const uint32_t*>(sc.tris + 3 * (size_t)h.tidx + 1) + 3);
+                key = min(mat, PT_KEY_BUCKETS - 1u);
+            }
+            w.hit[s] = make_float4(h.t, __uint_as_float(h.tidx), __uint_as_float(h.iidx), __uint_as_float(key));
+        }
+        if (do_hist) {   // warp-aggregated histogram: one atomic per distinct key per warp
+            uint32_t peers = __match_any_sync(PT_FULL, key);
+            if (valid && (uint32_t)(__ffs(peers) - 1) == pt_lane()) atomicAdd(&w.key_hist[key], (uint32_t)__popc(peers));
+        }
+    }
+}
+
+// B6: counting sort of the active list by material key.  key_hist holds counts -> exclusive offsets (one block).
+__global__ void __launch_bounds__(1024) k_key_scan(uint32_t* key_hist) {
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < PT_KEY_BUCKETS + 1u; b += 1024) {
+        uint32_t i = b + threadIdx.x;
+        uint32_t v = i < PT_KEY_BUCKETS + 1u ? key_hist[i] : 0, total;
+        uint32_t e = pt_block_excl_scan(v, &total);
+        if (i < PT_KEY_BUCKETS + 1u) key_hist[i] = carry + e;
+        carry += total;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_key_scatter(PtWave w) {
+    const uint32_t n = w.ctr->n_active;
+    const uint32_t rounds = (n + pt_gsize() - 1) / pt_gsize();
+    for (uint32_t r = 0; r < rounds; ++r) {
+        uint32_t j = r * pt_gsize() + pt_gtid();
+        bool valid = j < n;
+        uint32_t s = valid ? w.active[j] : 0u;
+        uint32_t key = valid ? __float_as_uint(w.hit[s].w) : (0xffff0000u + pt_lane());
+        // warp-aggregated slot claim: lanes with equal keys share one atomic
+        uint32_t peers = __match_any_sync(PT_FULL, key);
+        uint32_t leader = (uint32_t)__ffs(peers) - 1u, rank = __popc(peers & ((1u << pt_lane()) - 1u));
+        uint32_t base = 0;
+        if (valid && pt_lane() == leader) base = atomicAdd(&w.key_hist[key], (uint32_t)__popc(peers));
+        base = __shfl_sync(PT_FULL, base, leader);
+        if (valid) w.sorted[base + rank] = s;
+    }
+}
+__global__ void k_key_clear(uint32_t* key_hist) {
+    for (uint32_t i = pt_gtid(); i < PT_KEY_BUCKETS + 1u; i += pt_gsize()) key_hist[i] = 0;
+}
+
+struct PtShadeScene {
+    PtSceneView sv;
+    const PtMaterial* mats; uint32_t num_mats;
+    PtShadeConsts sc;
+};
+
+// B3 + B4 (+ the compaction half of B6): shade every active path; ballot/popc compaction of survivors and
+// of the emitted shadow rays (one atomic per warp each).
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(128) k_shade(PtShadeScene ss, PtWave w, const uint32_t* list) {
+    const uint32_t n = w.ctr->n_active;
+    const uint32_t rounds = (n + pt_gsize() - 1) / pt_gsize();
+    for (uint32_t r = 0; r < rounds; ++r) {
+        uint32_t j = r * pt_gsize() + pt_gtid();
+        bool valid = j < n, alive = false, shadow = false;
+        uint32_t s = 0;
+        PtShadowRay sh; sh.valid = false;
+        if (valid) {
+            s = list[j];
+            float4 o = w.ray_o[s], d = w.ray_d[s], be = w.beta[s], L = w.L[s], h = w.hit[s];
+            uint4 g = w.rng[s];
+            PtPath p;
+            p.o = pt_mk(o.x, o.y, o.z); p.d = pt_mk(d.x, d.y, d.z); p.beta = pt_mk(be.x, be.y, be.z); p.L = pt_mk(L.x, L.y, L.z);
+            p.rng.state = ((uint64_t)g.y << 32) | g.x; p.rng.inc = ((uint64_t)g.w << 32) | g.z;
+            p.pdf_prev = o.w; p.pixel = __float_as_uint(be.w); p.bounce = __float_as_uint(d.w);
+            uint32_t key = __float_as_uint(h.w);
+            if (key == PT_KEY_MISS) pt_shade_miss(&p, ss.sc);
+            else {
+                uint32_t tidx = __float_as_uint(h.y);
+                PtU4 t1 = pt_ldg4(ss.sv.tris + 3 * (size_t)tidx + 1), t2 = pt_ldg4(ss.sv.tris + 3 * (size_t)tidx + 2);
+                pt_v3 e1 = pt_mk(__uint_as_float(t1.x), __uint_as_float(t1.y), __uint_as_float(t1.z));
+                pt_v3 e2 = pt_mk(__uint_as_float(t2.x), __uint_as_float(t2.y), __uint_as_float(t2.z));
+                if (TWO_LEVEL) {
+                    const PtU4* ip = ss.sv.instances + 7 * (size_t)__float_as_uint(h.z);
+                    PtU4 m3 = pt_ldg4(ip + 3), m4 = pt_ldg4(ip + 4), m5 = pt_ldg4(ip + 5);
+                    float o2w[12] = {__uint_as_float(m3.x), __uint_as_float(m3.y), __uint_as_float(m3.z), __uint_as_float(m3.w),
+                                     __uint_as_float(m4.x), __uint_as_float(m4.y), __uint_as_float(m4.z), __uint_as_float(m4.w),
+                                     __uint_as_float(m5.x), __uint_as_float(m5.y), __uint_as_float(m5.z), __uint_as_float(m5.w)};
+                    e1 = pt_xform_vec(o2w, e1); e2 = pt_xform_vec(o2w, e2);
+                }
+                uint32_t mi = t1.w < ss.num_mats ? t1.w : 0u;
+                PtMaterial mat = ss.mats[mi];
+                alive = pt_shade_vertex(&p, ss.sc, h.x, e1, e2, mat, &sh);
+                shadow = sh.valid;
+            }
+            w.L[s] = make_float4(p.L.x, p.L.y, p.L.z, 0.0f);
+            if (alive) {
+                w.ray_o[s] = make_float4(p.o.x, p.o.y, p.o.z, p.pdf_prev);
+                w.ray_d[s] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(p.bounce));
+                w.beta[s] = make_float4(p.beta.x, p.beta.y, p.beta.z, be.w);
+                w.rng[s] = make_uint4((uint32_t)p.rng.state, (uint32_t)(p.rng.state >> 32), g.z, g.w);
+            }
+        }
+        // compaction: survivors -> next list
+        uint32_t am = __ballot_sync(PT_FULL, alive);
+        if (am) {
+            uint32_t base = 0;
+            if (pt_lane() == 0) base = atomicAdd(&w.ctr->n_next, (uint32_t)__popc(am));
+            base = __shfl_sync(PT_FULL, base, 0);
+            if (alive) w.next[base + __popc(am & ((1u << pt_lane()) - 1u))] = s;
+        }
+        // compaction: shadow rays -> shadow queue
+        uint32_t sm = __ballot_sync(PT_FULL, shadow);
+        if (sm) {
+            uint32_t base = 0;
+            if (pt_lane() == 0) base = atomicAdd(&w.ctr->n_shadow, (uint32_t)__popc(sm));
+            base = __shfl_sync(PT_FULL, base, 0);
+            if (shadow) {
+                uint32_t q = base + __popc(sm & ((1u << pt_lane()) - 1u));
+                w.sh_o[q] = make_float4(sh.o.x, sh.o.y, sh.o.z, sh.tmax);
+                w.sh_d[q] = make_float4(sh.d.x, sh.d.y, sh.d.z, __uint_as_float(s));
+                w.sh_c[q] = make_float4(sh.contrib.x, sh.contrib.y, sh.contrib.z, 0.0f);
+            }
+        }
+    }
+}
+
+// B5: connect — any-hit traversal of the shadow queue; unoccluded contributions are added to the path's L
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(128) k_connect(PtSceneView sc, PtWave w, uint32_t* status) {
+    const uint32_t n = w.ctr->n_shadow;
+    PtNoCount nc;
+    for (uint32_t q = pt_gtid(); q < n; q += pt_gsize()) {
+        float4 o = w.sh_o[q], d = w.sh_d[q];
+        PtHitRec h;
+        if (!pt_traverse<true, TWO_LEVEL>(sc, pt_mk(o.x, o.y, o.z), pt_mk(d.x, d.y, d.z), 0.0f, o.w, &h, nc)) atomicOr(status, 1u);
+        if (h.prim == PT_NONE) {
+            uint32_t s = __float_as_uint(d.w);
+            float4 c = w.sh_c[q], L = w.L[s];
+            w.L[s] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.0f);   // one shadow ray per slot per bounce: no atomics needed
+        }
+    }
+}
+
+// end of bounce: account rays, swap lists
+__global__ void k_bounce_end(PtWave w) {
+    if (pt_gtid() != 0) return;
+    w.ctr->total_extend += w.ctr->n_active; w.ctr->total_shadow += w.ctr->n_shadow;
+    w.ctr->n_active = w.ctr->n_next; w.ctr->n_next = 0; w.ctr->n_shadow = 0;
+}
+
+// B7: accumulate this sample of every slot into the frame (one add per pixel per sample: order fixed)
+__global__ void __launch_bounds__(256) k_accumulate(PtWave w, float4* accum) {
+    for (uint32_t s = pt_gtid(); s < w.num_slots; s += pt_gsize()) {
+        uint32_t pixel = w.slot_pixel ? w.slot_pixel[s] : s;
+        float4 L = w.L[s], a = accum[pixel];
+        accum[pixel] = make_float4(a.x + L.x, a.y + L.y, a.z + L.z, a.w + 1.0f);
+    }
+}
+__global__ void __launch_bounds__(256) k_resolve_rgba8(const float4* accum, uint32_t n, uint32_t* out) {
+    for (uint32_t i = pt_gtid(); i < n; i += pt_gsize()) {
+        float4 a = accum[i];
+        float inv = a.w > 0.0f ? pt_div(1.0f, a.w) : 0.0f;
+        uint32_t r = (uint32_t)(pt_clamp(a.x * inv, 0.0f, 1.0f) * 255.0f + 0.5f), g = (uint32_t)(pt_clamp(a.y * inv, 0.0f, 1.0f) * 255.0f + 0.5f),
+                 b = (uint32_t)(pt_clamp(a.z * inv, 0.0f, 1.0f) * 255.0f + 0.5f);
+        out[i] = r | (g << 8) | (b << 16) | (a.w > 0.0f ? 0xff000000u : 0u);
+    }
+}

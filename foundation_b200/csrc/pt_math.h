@@ -15,8 +15,10 @@
 
 #if defined(__CUDACC__)
 #define PT_HD __host__ __device__ __forceinline__
+#define PT_HDM __host__ __device__ __forceinline__
 #else
 #define PT_HD static inline __attribute__((always_inline))
+#define PT_HDM inline
 #endif
 
 // ---------------------------------------------------------------------------------------------

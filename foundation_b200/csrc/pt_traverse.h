@@ -32,8 +32,6 @@ struct PtSceneView {
     const PtU4* nodes;        // all BVH8 nodes: [TLAS | BLAS 0 | BLAS 1 ...] when two_level, else one BLAS
     const PtU4* tris;         // all triangles, 3 x 16 B each, BLAS after BLAS, leaf order
     const PtU4* instances;    // PtInstance records in TLAS leaf order, 7 x 16 B each (two_level only)
-    uint32_t two_level;
-    uint32_t root_tri_base;   // unused for two_level
 };
 
 struct PtRayCtx {
@@ -96,10 +94,11 @@ PT_HD uint32_t pt_node_hits(const PtU4& n0, const PtU4& n1, const PtU4& n2, cons
 struct PtHitRec {
     float t, U, V, ad;   // undivided barycentrics U, V and |det|
     uint32_t prim, inst;
+    uint32_t tidx, iidx;  // position of the triangle / instance record in the leaf-ordered device arrays (for shading)
 };
 
 template <class Counter>
-PT_HD void pt_test_tri(const PtU4* tris, uint32_t tri_index, const PtRayCtx& r, float tmin, uint32_t inst, PtHitRec* best, Counter& cnt) {
+PT_HD void pt_test_tri(const PtU4* tris, uint32_t tri_index, const PtRayCtx& r, float tmin, uint32_t inst, uint32_t iidx, PtHitRec* best, Counter& cnt) {
     const PtU4 a = tris[3 * (size_t)tri_index + 0], b = tris[3 * (size_t)tri_index + 1], c = tris[3 * (size_t)tri_index + 2];
     cnt.tri();
     float t, U, V, ad;
@@ -108,42 +107,39 @@ PT_HD void pt_test_tri(const PtU4* tris, uint32_t tri_index, const PtRayCtx& r, 
         uint64_t id = ((uint64_t)inst << 32) | a.w, bid = ((uint64_t)best->inst << 32) | best->prim;
         if (pt_closer(t, id, tmin, best->t, bid, best->prim != PT_NONE)) {
             best->t = t; best->U = U; best->V = V; best->ad = ad; best->prim = a.w; best->inst = inst;
+            best->tidx = tri_index; best->iidx = iidx;
         }
     }
 }
 
-struct PtNoCount { PT_HD void node() {} PT_HD void tri() {} PT_HD void inst() {} };
+struct PtNoCount { PT_HDM void node() {} PT_HDM void tri() {} PT_HDM void inst() {} };
 struct PtCount {
     uint64_t nodes, tris, insts;
-    PT_HD void node() { ++nodes; } PT_HD void tri() { ++tris; } PT_HD void inst() { ++insts; }
+    PT_HDM void node() { ++nodes; } PT_HDM void tri() { ++tris; } PT_HDM void inst() { ++insts; }
 };
 
 // ANY = true: occlusion query, returns as soon as any triangle is hit in (tmin, tmax).
 // Returns false on traversal-stack overflow (never observed; reported through the status word).
-template <bool ANY, class Counter>
+template <bool ANY, bool TWO_LEVEL, class Counter>
 PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best, Counter& cnt) {
     best->t = tmax; best->U = 0.0f; best->V = 0.0f; best->ad = 1.0f; best->prim = PT_NONE; best->inst = PT_NONE;
+    best->tidx = 0; best->iidx = 0;
     PtRayCtx world, r;
     pt_ray_ctx(&world, o, d);
     r = world;
     PtU2 stack[PT_STACK_SIZE];
     int sp = 0;
-    bool in_blas = !sc.two_level;
-    uint32_t node_base = 0, tri_base = 0, cur_inst = in_blas ? 0u : PT_NONE;
-    PtU2 ng; ng.x = 0; ng.y = 0x80000000u;   // root: pretend slot (7 ^ oct_inv) of a virtual parent with child_base 0
-    // the virtual parent's imask must make popc(...) == 0 for the root: handled by root flag below
-    bool root_pending = true;
+    bool in_blas = !TWO_LEVEL;
+    uint32_t node_base = 0, tri_base = 0, cur_inst = in_blas ? 0u : PT_NONE, cur_iidx = 0;
+    // root: one pending child of a virtual parent with child_base 0 and an empty imask, so popc(...) = 0 -> node 0
+    PtU2 ng; ng.x = 0; ng.y = 0x80000000u;
     PtU2 tg; tg.x = 0; tg.y = 0;
     for (;;) {
         if (ng.y & 0xff000000u) {
             uint32_t bit = 31u - (uint32_t)pt_clz32(ng.y);
             ng.y &= ~(1u << bit);
-            uint32_t child;
-            if (root_pending) { child = 0; root_pending = false; }
-            else {
-                uint32_t slot = (bit - 24u) ^ r.oct_inv;
-                child = ng.x + (uint32_t)pt_popc(ng.y & 0xffu & ~(0xffffffffu << slot));
-            }
+            uint32_t slot = (bit - 24u) ^ r.oct_inv;
+            uint32_t child = ng.x + (uint32_t)pt_popc(ng.y & 0xffu & ~(0xffffffffu << slot));
             if (ng.y & 0xff000000u) { if (sp >= PT_STACK_SIZE) return false; stack[sp++] = ng; }
             const PtU4* np = sc.nodes + 5 * (size_t)(node_base + child);
             const PtU4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
@@ -157,8 +153,8 @@ PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, floa
         while (tg.y) {
             uint32_t k = (uint32_t)pt_ffs0(tg.y);
             tg.y &= tg.y - 1u;
-            if (in_blas) {
-                pt_test_tri(sc.tris, tri_base + tg.x + k, r, tmin, cur_inst, best, cnt);
+            if (!TWO_LEVEL || in_blas) {
+                pt_test_tri(sc.tris, tri_base + tg.x + k, r, tmin, cur_inst, cur_iidx, best, cnt);
                 if (ANY && best->prim != PT_NONE) return true;
             } else {
                 // TLAS leaf: enter the instance.  Save the remaining groups, push the return sentinel.
@@ -172,9 +168,9 @@ PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, floa
                                  pt_u2f(m1.z), pt_u2f(m1.w), pt_u2f(m2.x), pt_u2f(m2.y), pt_u2f(m2.z), pt_u2f(m2.w)};
                 cnt.inst();
                 pt_ray_ctx(&r, pt_xform_point(w2o, world.o), pt_xform_vec(w2o, world.d));
-                node_base = m6.x; tri_base = m6.y; cur_inst = m6.w;   // m6 = node_base, tri_base, mesh_id, inst_id
+                node_base = m6.x; tri_base = m6.y; cur_inst = m6.w; cur_iidx = tg.x + k;   // m6 = node_base, tri_base, mesh_id, inst_id
                 in_blas = true;
-                ng.x = 0; ng.y = 0x80000000u; root_pending = true;
+                ng.x = 0; ng.y = 0x80000000u;
                 tg.x = 0; tg.y = 0;
             }
         }
@@ -182,7 +178,7 @@ PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, floa
             for (;;) {
                 if (sp == 0) return true;
                 ng = stack[--sp];
-                if (ng.x == PT_NONE && ng.y == 0) {   // leaving an instance
+                if (TWO_LEVEL && ng.x == PT_NONE && ng.y == 0) {   // leaving an instance
                     r = world; in_blas = false; node_base = 0; tri_base = 0; cur_inst = PT_NONE;
                     continue;
                 }

@@ -1,0 +1,172 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.  Gates (north_star): hit IDs bit-exact with ties by primitive index, t within 2 ulp (we expect 0),
+image RMSE <= 1e-3 on linear radiance (we expect bit-identical).  Marked gpu: run on the B200 box."""
+import numpy as np
+import pytest
+
+from foundation_b200 import pt, scenes
+from oracle.pt_oracle import OracleScene
+from tests.util import SMALL_SCENES, assert_hits_equal, ray_mix, rmse
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=list(SMALL_SCENES))
+def pair(request, gpu):
+    sc = SMALL_SCENES[request.param]()
+    tr = pt.PathTracer(sc.width, sc.height, seed=1, background=sc.background)
+    tr.load(sc)
+    yield request.param, sc, tr, OracleScene(sc)
+    tr.close()
+
+
+def test_build_is_byte_identical_to_oracle(pair):
+    """A1-A6: device radix sort + Karras emit + refit + collapse produce the oracle's BVH8 byte for byte."""
+    name, sc, tr, orc = pair
+    for mid in range(len(sc.meshes)):
+        gn, gt, go = tr.blas_download(mid)
+        on, ot, oo = orc.blas(mid)
+        assert np.array_equal(go, oo), f"{name}: Morton order differs (radix sort / keys)"
+        assert len(gn) == len(on) and gn.tobytes() == on.tobytes(), f"{name}: BVH8 nodes differ"
+        assert gt.tobytes() == ot.tobytes(), f"{name}: leaf-ordered triangles differ"
+    if sc.instances is not None:
+        gn, go = tr.tlas_download()
+        on, oo, _ = orc.tlas()
+        assert np.array_equal(go, oo) and gn.tobytes() == on.tobytes(), f"{name}: TLAS differs"
+
+
+def test_closest_hit_matches_oracle_bvh_and_brute_force(pair):
+    name, sc, tr, orc = pair
+    rays = ray_mix(sc)
+    gh, gi = tr.trace_closest(rays)
+    oh, oi = orc.trace_closest(rays)
+    assert_hits_equal(gh, gi, oh, oi, f"{name} vs oracle BVH")
+    assert gh.tobytes() == oh.tobytes(), f"{name}: t/u/v not bit-identical"
+    n = 512 if sc.effective_triangles > 200000 else 4096
+    bh, bi = orc.trace_closest(rays[:n], brute=True)
+    assert_hits_equal(gh[:n], gi[:n], bh, bi, f"{name} vs CPU brute force")
+    # device-side exhaustive kernel on the whole set
+    tr.rays_upload(rays)
+    tr.rays_trace_brute()
+    dh, di = tr.rays_download_hits()
+    assert_hits_equal(gh, gi, dh, di, f"{name} vs device brute force")
+
+
+def test_any_hit_matches_oracle(pair):
+    name, sc, tr, orc = pair
+    rays = ray_mix(sc)
+    assert np.array_equal(tr.trace_any(rays), orc.trace_any(rays)), f"{name}: occlusion differs"
+
+
+def test_device_resident_path_equals_host_path(pair):
+    name, sc, tr, orc = pair
+    rays = ray_mix(sc, 2048)
+    gh, gi = tr.trace_closest(rays)
+    tr.rays_upload(rays)
+    tr.rays_trace_closest()
+    dh, di = tr.rays_download_hits()
+    assert gh.tobytes() == dh.tobytes() and np.array_equal(gi, di)
+    st = tr.stats()
+    assert st.kernel_launches >= 1 and st.last_ms > 0
+
+
+@pytest.mark.parametrize("flags", [0, pt.FLAG_NO_MATERIAL_SORT])
+def test_image_matches_oracle(pair, flags):
+    """B1-B7: the wavefront loop (queues, compaction, material sort) against one scalar loop per path."""
+    name, sc, _, orc = pair
+    spp, bounces = 2, 4
+    tr = pt.PathTracer(sc.width, sc.height, seed=7, flags=flags, background=sc.background)
+    tr.load(sc)
+    tr.render(0, 1, bounces)
+    tr.render(1, spp - 1, bounces)          # progressive: second call continues the accumulation
+    g = tr.read_accum()
+    st = tr.stats()
+    rc = np.zeros(2, np.uint64)
+    o = orc.render(sc.width, sc.height, 7, 0, spp, bounces, flags=flags, background=sc.background, ray_counts=rc)
+    e = rmse(g[..., :3] / spp, o[..., :3] / spp)
+    differing = int((g != o).any(axis=-1).sum())
+    print(f"{name} flags={flags}: rmse={e:.3e} differing_pixels={differing} mean={o[..., :3].mean() / spp:.4f}")
+    assert e <= 1e-3, f"{name}: image RMSE {e}"
+    assert differing == 0, f"{name}: {differing} pixels not bit-identical"
+    assert np.all(g[..., 3] == spp)
+    tr.close()
+
+
+def test_tile_partition_is_bit_identical(pair):
+    """§8e: interleaved tiles -> the union of the ranks' images equals the single-GPU image exactly."""
+    name, sc, _, orc = pair
+    full = pt.PathTracer(sc.width, sc.height, seed=3, background=sc.background); full.load(sc)
+    full.render(0, 1, 3)
+    ref = full.read_accum(); full.close()
+    total = np.zeros_like(ref)
+    for rank in range(3):
+        t = pt.PathTracer(sc.width, sc.height, seed=3, background=sc.background); t.load(sc)
+        t.partition_set(rank, 3, 16)
+        t.render(0, 1, 3)
+        part = t.read_accum(); t.close()
+        assert np.all((part[..., 3] == 0) | (total[..., 3] == 0)), "tiles overlap"
+        total += part
+        o = orc.render(sc.width, sc.height, 3, 0, 1, 3, background=sc.background, rank=rank, count=3, tile=16)
+        assert np.array_equal(part, o), f"{name}: rank {rank} differs from oracle partition"
+    assert np.array_equal(total, ref)
+
+
+def test_resolve_rgba8(pair):
+    name, sc, tr, _ = pair
+    tr.render(0, 2, 2)
+    acc = tr.read_accum()
+    img = tr.resolve_rgba8()
+    want = (np.clip(acc[..., :3] / acc[..., 3:4], 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    assert np.abs(img[..., :3].astype(int) - want.astype(int)).max() <= 1
+    assert np.all(img[..., 3] == 255)
+
+
+def test_vertex_formats(gpu):
+    """R16_UINT / R32_UINT / unindexed, and an over-aligned vertex stride (reference: vertex_input, Renderer.cpp:23-27,110-115)."""
+    sc = scenes.cornell_box(64, 64)
+    m = sc.meshes[0]
+    rays = ray_mix(sc, 1024)
+    outs = []
+    for variant in ("u32", "u16", "soup", "stride32"):
+        t = pt.PathTracer(64, 64)
+        t.materials_set(sc.materials)
+        if variant == "u32":
+            t.mesh_create(m.positions, m.indices, m.material_ids)
+        elif variant == "u16":
+            t.mesh_create(m.positions, m.indices.astype(np.uint16), m.material_ids)
+        elif variant == "soup":
+            t.mesh_create(m.positions[m.indices.reshape(-1)], None, m.material_ids)
+        else:
+            padded = np.zeros((m.positions.shape[0], 8), np.float32); padded[:, :3] = m.positions; padded[:, 3:] = 7.0
+            t.mesh_create(padded, m.indices, m.material_ids, stride=32)
+        t.scene_commit()
+        outs.append(t.trace_closest(rays)[0])
+        t.close()
+    for o in outs[1:]:
+        assert o.tobytes() == outs[0].tobytes()
+
+
+def test_error_behaviour(gpu):
+    """C ABI never throws: bad arguments / call order give negative status + message (SURVEY.md §8b error convention)."""
+    t = pt.PathTracer(32, 32)
+    with pytest.raises(pt.FoundationPtError) as e:
+        t.render(0, 1, 1)
+    assert e.value.status == pt.ERR_STATE
+    with pytest.raises(pt.FoundationPtError) as e:
+        t.mesh_create(np.zeros((3, 3), np.float32), np.asarray([[0, 1, 5]], np.uint32))
+    assert e.value.status == pt.ERR_ARGUMENT
+    with pytest.raises(pt.FoundationPtError) as e:
+        t.scene_commit()
+    assert e.value.status == pt.ERR_STATE
+    t.mesh_create(np.asarray([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.asarray([[0, 1, 2]], np.uint32))
+    t.scene_commit()
+    with pytest.raises(pt.FoundationPtError):
+        t.render(0, 1, 1)            # camera not set
+    # single-triangle scene, empty ray set, degenerate rays
+    hits, _ = t.trace_closest(np.zeros(0, scenes.RAY_DTYPE))
+    assert len(hits) == 0
+    r = np.zeros(3, scenes.RAY_DTYPE)
+    r["origin"] = [(0.2, 0.2, 1), (0.2, 0.2, 1), (5, 5, 1)]; r["direction"] = [(0, 0, -1), (0, 0, 0), (0, 0, -1)]; r["tmax"] = np.inf
+    hits, _ = t.trace_closest(r)
+    assert hits["prim"][0] == 0 and hits["t"][0] == 1.0 and hits["prim"][1] == 0xFFFFFFFF and hits["prim"][2] == 0xFFFFFFFF
+    t.close()
