@@ -62,7 +62,7 @@ struct Mesh {
 struct foundation_pt_context {
     foundation_pt_config cfg{};
     foundation_pt_allocator host_alloc{};
-    int device = 0, num_sms = 0;
+    int device = 0, num_sms = 0, trace_blocks_per_sm = 8, fetch_thresh = 24;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     mutable std::string err = "no error";
@@ -263,10 +263,11 @@ int32_t check_status(Ctx* ctx) {
 template <bool ANY>
 int32_t launch_trace(Ctx* ctx, const float4* rays, uint64_t n, float4* hits, uint32_t* inst, uint8_t* occ) {
     if (n == 0) return 0;
-    int per_sm = 8;
-    uint32_t grid = grid_for(ctx, n, 128, per_sm);
-    if (ctx->two_level) PT_LAUNCH(ctx, (k_trace_rays<ANY, true, false>), grid, 128, ctx->view, rays, (unsigned long long)n, hits, inst, occ, ctx->d_status.as<uint32_t>(), nullptr);
-    else PT_LAUNCH(ctx, (k_trace_rays<ANY, false, false>), grid, 128, ctx->view, rays, (unsigned long long)n, hits, inst, occ, ctx->d_status.as<uint32_t>(), nullptr);
+    uint32_t grid = grid_for(ctx, n, 128, ctx->trace_blocks_per_sm);
+    unsigned long long* wc = reinterpret_cast<unsigned long long*>(ctx->d_status.as<uint32_t>() + 2);
+    PT_CK(cudaMemsetAsync(wc, 0, 8, ctx->stream));
+    if (ctx->two_level) PT_LAUNCH(ctx, (k_trace_rays<ANY, true, false>), grid, 128, ctx->view, rays, (unsigned long long)n, hits, inst, occ, ctx->d_status.as<uint32_t>(), nullptr, wc, ctx->fetch_thresh);
+    else PT_LAUNCH(ctx, (k_trace_rays<ANY, false, false>), grid, 128, ctx->view, rays, (unsigned long long)n, hits, inst, occ, ctx->d_status.as<uint32_t>(), nullptr, wc, ctx->fetch_thresh);
     PT_CK(cudaGetLastError());
     return 0;
 }
@@ -324,7 +325,7 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
     ss.sc.bg[0] = ctx->cfg.background[0]; ss.sc.bg[1] = ctx->cfg.background[1]; ss.sc.bg[2] = ctx->cfg.background[2];
     const bool sort = !(ctx->cfg.flags & FOUNDATION_PT_FLAG_NO_MATERIAL_SORT);
     const uint32_t S = ctx->num_slots;
-    const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8);
+    const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8), gtrace = grid_for(ctx, S, 128, ctx->trace_blocks_per_sm);
     uint32_t* status = ctx->d_status.as<uint32_t>();
     for (uint32_t smp = s0; smp < s0 + ns; ++smp) {
         PtFrame f; f.cam = ctx->cam; f.seed = ctx->cfg.seed; f.width = ctx->cfg.width; f.height = ctx->cfg.height; f.sample = smp;
@@ -332,15 +333,16 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
         PT_LAUNCH(ctx, k_raygen, g256, 256, w, f);
         for (uint32_t b = 0; b <= max_bounces; ++b) {
             if (sort) PT_LAUNCH(ctx, k_key_clear, 2, 1024, w.key_hist);
-            PT_LAUNCH(ctx, k_extend<TWO>, g128, 128, ctx->view, w, status, sort ? 1 : 0);
+            PT_LAUNCH(ctx, k_extend<TWO>, gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
             const uint32_t* list = w.active;
             if (sort) {
+                PT_LAUNCH(ctx, k_key_hist, g256, 256, w);
                 PT_LAUNCH(ctx, k_key_scan, 1, 1024, w.key_hist);
                 PT_LAUNCH(ctx, k_key_scatter, g256, 256, w);
                 list = w.sorted;
             }
             PT_LAUNCH(ctx, k_shade<TWO>, g128, 128, ss, w, list);
-            PT_LAUNCH(ctx, k_connect<TWO>, g128, 128, ctx->view, w, status);
+            PT_LAUNCH(ctx, k_connect<TWO>, gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
             PT_LAUNCH(ctx, k_bounce_end, 1, 32, w);
             std::swap(w.active, w.next);
         }
@@ -397,6 +399,8 @@ int32_t foundation_pt_create(const foundation_pt_config* config, const foundatio
         return FOUNDATION_PT_ERR_CUDA;
     }
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("FOUNDATION_PT_FETCH_THRESH")) { int v = atoi(e); if (v >= 0 && v <= 32) ctx->fetch_thresh = v; }
+    if (const char* e = getenv("FOUNDATION_PT_TRACE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->trace_blocks_per_sm = v; }
     ctx->mats.push_back(PtMaterial{0.8f, 0.8f, 0.8f, 0.5f, 0, 0, 0, 0});
     *out_ctx = ctx;
     return FOUNDATION_PT_OK;

@@ -339,31 +339,87 @@ __global__ void __launch_bounds__(256) k_write_instances(const PtInstance* in, u
 // ---------------------------------------------------------------------------------------------------
 struct PtDevCounters { unsigned long long nodes, tris, insts; };
 
-template <bool ANY, bool TWO_LEVEL, bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_rays(PtSceneView sc, const float4* __restrict__ rays, unsigned long long n, float4* __restrict__ hits,
-                                                    uint32_t* __restrict__ inst_out, uint8_t* __restrict__ occ, uint32_t* status, PtDevCounters* counters) {
-    PtCount cnt; cnt.nodes = cnt.tris = cnt.insts = 0;
-    PtNoCount nocnt;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
-        PtHitRec h;
-        bool ok;
-        if (COUNT) ok = pt_traverse<ANY, TWO_LEVEL>(sc, pt_mk(a.x, a.y, a.z), pt_mk(b.x, b.y, b.z), a.w, b.w, &h, cnt);
-        else ok = pt_traverse<ANY, TWO_LEVEL>(sc, pt_mk(a.x, a.y, a.z), pt_mk(b.x, b.y, b.z), a.w, b.w, &h, nocnt);
-        if (!ok) atomicOr(status, 1u);
-        if (ANY) occ[i] = h.prim != PT_NONE ? 1 : 0;
-        else {
-            float4 o;
-            if (h.prim == PT_NONE) { o.x = __uint_as_float(PT_INF_BITS); o.y = 0.0f; o.z = 0.0f; }
-            else { o.x = h.t; o.y = pt_div(h.U, h.ad); o.z = pt_div(h.V, h.ad); }
-            o.w = __uint_as_float(h.prim);
-            hits[i] = o;
-            if (inst_out) inst_out[i] = h.inst;
+// Warp-persistent traversal with dynamic ray fetch (Aila & Laine 2009 "persistent while-while"): every lane
+// owns one ray at a time; when fewer than THRESH lanes of the warp are still traversing, the idle lanes claim
+// new work items from a global counter with ONE atomic per warp (ballot + popc + shfl), so a few long rays no
+// longer hold 31 finished lanes hostage.  Job supplies load(i) -> ray and store(i, hit).
+#ifndef PT_FETCH_THRESH
+#define PT_FETCH_THRESH 20
+#endif
+template <bool ANY, bool TWO_LEVEL, class Counter, class Job>
+__device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, unsigned long long n, unsigned long long* work_counter, uint32_t* status,
+                                              Counter& cnt, int fetch_thresh) {
+    PtTravState st;
+    PtU2 stack[PT_STACK_SIZE];
+    PtHitRec best;
+    bool active = false, drained = false;   // drained: the global queue is empty (warp-uniform once set)
+    unsigned long long idx = 0;
+    const uint32_t lane = pt_lane();
+    for (;;) {
+        uint32_t need = __ballot_sync(PT_FULL, !active);
+        if (need && !drained) {
+            uint32_t leader = (uint32_t)__ffs(need) - 1u;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(PT_FULL, base, leader);
+            bool got_none = false;
+            if (!active) {
+                idx = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
+                if (idx < n) {
+                    pt_v3 o, d; float tmin, tmax;
+                    job.load(idx, &o, &d, &tmin, &tmax);
+                    pt_trav_init<TWO_LEVEL>(&st, o, d, tmin, tmax, &best);
+                    active = true;
+                } else got_none = true;
+            }
+            drained = __any_sync(PT_FULL, got_none);
+        }
+        if (!__any_sync(PT_FULL, active)) break;
+        while (active) {
+            if (pt_trav_step<ANY, TWO_LEVEL>(sc, &st, stack, &best, cnt) == PT_STEP_DONE) {
+                if (st.overflow) atomicOr(status, 1u);
+                job.store(idx, best);
+                active = false;
+                break;
+            }
+            if (!drained && __popc(__activemask()) < fetch_thresh) break;
         }
     }
+}
+
+// B2 / B5 on explicit ray sets: 32-byte ray records read with two 128-bit loads, 16-byte hit records written
+// with one 128-bit store.
+template <bool ANY>
+struct PtRaySetJob {
+    const float4* __restrict__ rays; float4* __restrict__ hits; uint32_t* __restrict__ inst_out; uint8_t* __restrict__ occ;
+    __device__ __forceinline__ void load(unsigned long long i, pt_v3* o, pt_v3* d, float* tmin, float* tmax) const {
+        float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+        *o = pt_mk(a.x, a.y, a.z); *d = pt_mk(b.x, b.y, b.z); *tmin = a.w; *tmax = b.w;
+    }
+    __device__ __forceinline__ void store(unsigned long long i, const PtHitRec& h) const {
+        if (ANY) { occ[i] = h.prim != PT_NONE ? 1 : 0; return; }
+        float4 o;
+        if (h.prim == PT_NONE) { o.x = __uint_as_float(PT_INF_BITS); o.y = 0.0f; o.z = 0.0f; }
+        else { o.x = h.t; o.y = pt_div(h.U, h.ad); o.z = pt_div(h.V, h.ad); }
+        o.w = __uint_as_float(h.prim);
+        hits[i] = o;
+        if (inst_out) inst_out[i] = h.inst;
+    }
+};
+
+template <bool ANY, bool TWO_LEVEL, bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_rays(PtSceneView sc, const float4* __restrict__ rays, unsigned long long n, float4* __restrict__ hits,
+                                                    uint32_t* __restrict__ inst_out, uint8_t* __restrict__ occ, uint32_t* status, PtDevCounters* counters,
+                                                    unsigned long long* work_counter, int fetch_thresh) {
+    PtRaySetJob<ANY> job; job.rays = rays; job.hits = hits; job.inst_out = inst_out; job.occ = occ;
     if (COUNT) {
+        PtCount cnt; cnt.nodes = cnt.tris = cnt.insts = 0;
+        pt_warp_trace<ANY, TWO_LEVEL>(sc, job, n, work_counter, status, cnt, fetch_thresh);
         atomicAdd(&counters->nodes, (unsigned long long)cnt.nodes); atomicAdd(&counters->tris, (unsigned long long)cnt.tris);
         atomicAdd(&counters->insts, (unsigned long long)cnt.insts);
+    } else {
+        PtNoCount nc;
+        pt_warp_trace<ANY, TWO_LEVEL>(sc, job, n, work_counter, status, nc, fetch_thresh);
     }
 }
 
@@ -413,6 +469,7 @@ __global__ void __launch_bounds__(128) k_trace_brute(PtSceneView sc, const PtIns
 struct PtWaveCounters {
     uint32_t n_active, n_next, n_shadow, pad;
     unsigned long long total_extend, total_shadow;
+    unsigned long long work_extend, work_connect;   // dynamic-fetch cursors of the two traversal kernels
 };
 struct PtWave {
     float4* ray_o;     // o.xyz, pdf_prev
@@ -452,35 +509,44 @@ __global__ void __launch_bounds__(256) k_raygen(PtWave w, PtFrame f) {
         w.rng[s] = make_uint4((uint32_t)p.rng.state, (uint32_t)(p.rng.state >> 32), (uint32_t)p.rng.inc, (uint32_t)(p.rng.inc >> 32));
         w.active[s] = s;
     }
-    if (pt_gtid() == 0) { w.ctr->n_active = w.num_slots; w.ctr->n_next = 0; w.ctr->n_shadow = 0; }
+    if (pt_gtid() == 0) { w.ctr->n_active = w.num_slots; w.ctr->n_next = 0; w.ctr->n_shadow = 0; w.ctr->work_extend = 0; w.ctr->work_connect = 0; }
 }
 
-// B2: extend — closest hit for every active path; also emits the material sort key and its histogram
+// B2: extend — closest hit for every active path (warp-persistent, dynamic fetch over the active list);
+// writes the hit record with the material sort key.
+struct PtExtendJob {
+    PtWave w; const PtU4* tris;
+    __device__ __forceinline__ void load(unsigned long long j, pt_v3* o, pt_v3* d, float* tmin, float* tmax) const {
+        uint32_t s = w.active[j];
+        float4 a = w.ray_o[s], b = w.ray_d[s];
+        *o = pt_mk(a.x, a.y, a.z); *d = pt_mk(b.x, b.y, b.z); *tmin = 0.0f; *tmax = __uint_as_float(PT_INF_BITS);
+    }
+    __device__ __forceinline__ void store(unsigned long long j, const PtHitRec& h) const {
+        uint32_t s = w.active[j];
+        uint32_t key = PT_KEY_MISS;
+        if (h.prim != PT_NONE) {
+            uint32_t mat = __ldg(reinterpret_cast<const uint32_t*>(tris + 3 * (size_t)h.tidx + 1) + 3);
+            key = min(mat, PT_KEY_BUCKETS - 1u);
+        }
+        w.hit[s] = make_float4(h.t, __uint_as_float(h.tidx), __uint_as_float(h.iidx), __uint_as_float(key));
+    }
+};
 template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(128) k_extend(PtSceneView sc, PtWave w, uint32_t* status, int do_hist) {
+__global__ void __launch_bounds__(128) k_extend(PtSceneView sc, PtWave w, uint32_t* status, int fetch_thresh) {
+    PtExtendJob job; job.w = w; job.tris = sc.tris;
+    PtNoCount nc;
+    pt_warp_trace<false, TWO_LEVEL>(sc, job, (unsigned long long)w.ctr->n_active, &w.ctr->work_extend, status, nc, fetch_thresh);
+}
+// histogram of the sort keys (warp-aggregated: one atomic per distinct key per warp)
+__global__ void __launch_bounds__(256) k_key_hist(PtWave w) {
     const uint32_t n = w.ctr->n_active;
     const uint32_t rounds = (n + pt_gsize() - 1) / pt_gsize();
-    PtNoCount nc;
     for (uint32_t r = 0; r < rounds; ++r) {
         uint32_t j = r * pt_gsize() + pt_gtid();
         bool valid = j < n;
-        uint32_t key = 0xffff0000u + pt_lane();   // invalid lanes: unique keys, never counted
-        if (valid) {
-            uint32_t s = w.active[j];
-            float4 o = w.ray_o[s], d = w.ray_d[s];
-            PtHitRec h;
-            if (!pt_traverse<false, TWO_LEVEL>(sc, pt_mk(o.x, o.y, o.z), pt_mk(d.x, d.y, d.z), 0.0f, __uint_as_float(PT_INF_BITS), &h, nc)) atomicOr(status, 1u);
-            key = PT_KEY_MISS;
-            if (h.prim != PT_NONE) {
-                uint32_t mat = __ldg(reinterpret_cast<const uint32_t*>(sc.tris + 3 * (size_t)h.tidx + 1) + 3);
-                key = min(mat, PT_KEY_BUCKETS - 1u);
-            }
-            w.hit[s] = make_float4(h.t, __uint_as_float(h.tidx), __uint_as_float(h.iidx), __uint_as_float(key));
-        }
-        if (do_hist) {   // warp-aggregated histogram: one atomic per distinct key per warp
-            uint32_t peers = __match_any_sync(PT_FULL, key);
-            if (valid && (uint32_t)(__ffs(peers) - 1) == pt_lane()) atomicAdd(&w.key_hist[key], (uint32_t)__popc(peers));
-        }
+        uint32_t key = valid ? __float_as_uint(w.hit[w.active[j]].w) : (0xffff0000u + pt_lane());
+        uint32_t peers = __match_any_sync(PT_FULL, key);
+        if (valid && (uint32_t)(__ffs(peers) - 1) == pt_lane()) atomicAdd(&w.key_hist[key], (uint32_t)__popc(peers));
     }
 }
 
@@ -595,27 +661,31 @@ __global__ void __launch_bounds__(128) k_shade(PtShadeScene ss, PtWave w, const 
 }
 
 // B5: connect — any-hit traversal of the shadow queue; unoccluded contributions are added to the path's L
-template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(128) k_connect(PtSceneView sc, PtWave w, uint32_t* status) {
-    const uint32_t n = w.ctr->n_shadow;
-    PtNoCount nc;
-    for (uint32_t q = pt_gtid(); q < n; q += pt_gsize()) {
-        float4 o = w.sh_o[q], d = w.sh_d[q];
-        PtHitRec h;
-        if (!pt_traverse<true, TWO_LEVEL>(sc, pt_mk(o.x, o.y, o.z), pt_mk(d.x, d.y, d.z), 0.0f, o.w, &h, nc)) atomicOr(status, 1u);
-        if (h.prim == PT_NONE) {
-            uint32_t s = __float_as_uint(d.w);
-            float4 c = w.sh_c[q], L = w.L[s];
-            w.L[s] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.0f);   // one shadow ray per slot per bounce: no atomics needed
-        }
+struct PtConnectJob {
+    PtWave w;
+    __device__ __forceinline__ void load(unsigned long long q, pt_v3* o, pt_v3* d, float* tmin, float* tmax) const {
+        float4 a = w.sh_o[q], b = w.sh_d[q];
+        *o = pt_mk(a.x, a.y, a.z); *d = pt_mk(b.x, b.y, b.z); *tmin = 0.0f; *tmax = a.w;
     }
+    __device__ __forceinline__ void store(unsigned long long q, const PtHitRec& h) const {
+        if (h.prim != PT_NONE) return;
+        uint32_t s = __float_as_uint(w.sh_d[q].w);
+        float4 c = w.sh_c[q], L = w.L[s];
+        w.L[s] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.0f);   // one shadow ray per slot per bounce: no atomics needed
+    }
+};
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(128) k_connect(PtSceneView sc, PtWave w, uint32_t* status, int fetch_thresh) {
+    PtConnectJob job; job.w = w;
+    PtNoCount nc;
+    pt_warp_trace<true, TWO_LEVEL>(sc, job, (unsigned long long)w.ctr->n_shadow, &w.ctr->work_connect, status, nc, fetch_thresh);
 }
 
 // end of bounce: account rays, swap lists
 __global__ void k_bounce_end(PtWave w) {
     if (pt_gtid() != 0) return;
     w.ctr->total_extend += w.ctr->n_active; w.ctr->total_shadow += w.ctr->n_shadow;
-    w.ctr->n_active = w.ctr->n_next; w.ctr->n_next = 0; w.ctr->n_shadow = 0;
+    w.ctr->n_active = w.ctr->n_next; w.ctr->n_next = 0; w.ctr->n_shadow = 0; w.ctr->work_extend = 0; w.ctr->work_connect = 0;
 }
 
 // B7: accumulate this sample of every slot into the frame (one add per pixel per sample: order fixed)

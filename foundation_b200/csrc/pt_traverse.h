@@ -118,72 +118,99 @@ struct PtCount {
     PT_HDM void node() { ++nodes; } PT_HDM void tri() { ++tris; } PT_HDM void inst() { ++insts; }
 };
 
-// ANY = true: occlusion query, returns as soon as any triangle is hit in (tmin, tmax).
-// Returns false on traversal-stack overflow (never observed; reported through the status word).
-template <bool ANY, bool TWO_LEVEL, class Counter>
-PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best, Counter& cnt) {
+// Resumable traversal state: pt_trav_init + repeated pt_trav_step (one node visit, its triangles, one pop).
+// The kernels interleave steps with warp-level dynamic ray fetch; pt_traverse below is init + loop and is what
+// the emulation harness runs.
+struct PtTravState {
+    PtRayCtx world, r;
+    float tmin;
+    PtU2 ng, tg;
+    uint32_t node_base, tri_base, cur_inst, cur_iidx;
+    int sp;
+    bool in_blas, overflow;
+};   // the group stack is a separate array so this struct stays in registers
+enum { PT_STEP_RUNNING = 0, PT_STEP_DONE = 1 };
+
+template <bool TWO_LEVEL>
+PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best) {
     best->t = tmax; best->U = 0.0f; best->V = 0.0f; best->ad = 1.0f; best->prim = PT_NONE; best->inst = PT_NONE;
     best->tidx = 0; best->iidx = 0;
-    PtRayCtx world, r;
-    pt_ray_ctx(&world, o, d);
-    r = world;
-    PtU2 stack[PT_STACK_SIZE];
-    int sp = 0;
-    bool in_blas = !TWO_LEVEL;
-    uint32_t node_base = 0, tri_base = 0, cur_inst = in_blas ? 0u : PT_NONE, cur_iidx = 0;
+    pt_ray_ctx(&s->world, o, d);
+    s->r = s->world;
+    s->tmin = tmin;
+    s->sp = 0; s->overflow = false;
+    s->in_blas = !TWO_LEVEL;
+    s->node_base = 0; s->tri_base = 0; s->cur_inst = TWO_LEVEL ? PT_NONE : 0u; s->cur_iidx = 0;
     // root: one pending child of a virtual parent with child_base 0 and an empty imask, so popc(...) = 0 -> node 0
-    PtU2 ng; ng.x = 0; ng.y = 0x80000000u;
-    PtU2 tg; tg.x = 0; tg.y = 0;
-    for (;;) {
-        if (ng.y & 0xff000000u) {
-            uint32_t bit = 31u - (uint32_t)pt_clz32(ng.y);
-            ng.y &= ~(1u << bit);
-            uint32_t slot = (bit - 24u) ^ r.oct_inv;
-            uint32_t child = ng.x + (uint32_t)pt_popc(ng.y & 0xffu & ~(0xffffffffu << slot));
-            if (ng.y & 0xff000000u) { if (sp >= PT_STACK_SIZE) return false; stack[sp++] = ng; }
-            const PtU4* np = sc.nodes + 5 * (size_t)(node_base + child);
-            const PtU4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
-            cnt.node();
-            uint32_t hits = pt_node_hits(n0, n1, n2, n3, n4, r, tmin, best->t);
-            ng.x = n1.x; ng.y = (hits & 0xff000000u) | (n0.w >> 24);
-            tg.x = n1.y; tg.y = hits & 0x00ffffffu;
+    s->ng.x = 0; s->ng.y = 0x80000000u;
+    s->tg.x = 0; s->tg.y = 0;
+}
+
+// ANY = true: occlusion query, finishes as soon as any triangle is hit in (tmin, tmax).
+template <bool ANY, bool TWO_LEVEL, class Counter>
+PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHitRec* best, Counter& cnt) {
+    if (s->ng.y & 0xff000000u) {
+        uint32_t bit = 31u - (uint32_t)pt_clz32(s->ng.y);
+        s->ng.y &= ~(1u << bit);
+        uint32_t slot = (bit - 24u) ^ s->r.oct_inv;
+        uint32_t child = s->ng.x + (uint32_t)pt_popc(s->ng.y & 0xffu & ~(0xffffffffu << slot));
+        if (s->ng.y & 0xff000000u) {
+            if (s->sp >= PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
+            stack[s->sp++] = s->ng;
+        }
+        const PtU4* np = sc.nodes + 5 * (size_t)(s->node_base + child);
+        const PtU4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+        cnt.node();
+        uint32_t hits = pt_node_hits(n0, n1, n2, n3, n4, s->r, s->tmin, best->t);
+        s->ng.x = n1.x; s->ng.y = (hits & 0xff000000u) | (n0.w >> 24);
+        s->tg.x = n1.y; s->tg.y = hits & 0x00ffffffu;
+    } else {
+        s->tg = s->ng; s->ng.x = 0; s->ng.y = 0;
+    }
+    while (s->tg.y) {
+        uint32_t k = (uint32_t)pt_ffs0(s->tg.y);
+        s->tg.y &= s->tg.y - 1u;
+        if (!TWO_LEVEL || s->in_blas) {
+            pt_test_tri(sc.tris, s->tri_base + s->tg.x + k, s->r, s->tmin, s->cur_inst, s->cur_iidx, best, cnt);
+            if (ANY && best->prim != PT_NONE) return PT_STEP_DONE;
         } else {
-            tg = ng; ng.x = 0; ng.y = 0;
-        }
-        while (tg.y) {
-            uint32_t k = (uint32_t)pt_ffs0(tg.y);
-            tg.y &= tg.y - 1u;
-            if (!TWO_LEVEL || in_blas) {
-                pt_test_tri(sc.tris, tri_base + tg.x + k, r, tmin, cur_inst, cur_iidx, best, cnt);
-                if (ANY && best->prim != PT_NONE) return true;
-            } else {
-                // TLAS leaf: enter the instance.  Save the remaining groups, push the return sentinel.
-                if (sp + 3 > PT_STACK_SIZE) return false;
-                if (tg.y) stack[sp++] = tg;
-                if (ng.y & 0xff000000u) stack[sp++] = ng;
-                PtU2 sentinel; sentinel.x = PT_NONE; sentinel.y = 0; stack[sp++] = sentinel;
-                const PtU4* ip = sc.instances + 7 * (size_t)(tg.x + k);
-                PtU4 m0 = ip[0], m1 = ip[1], m2 = ip[2], m6 = ip[6];
-                float w2o[12] = {pt_u2f(m0.x), pt_u2f(m0.y), pt_u2f(m0.z), pt_u2f(m0.w), pt_u2f(m1.x), pt_u2f(m1.y),
-                                 pt_u2f(m1.z), pt_u2f(m1.w), pt_u2f(m2.x), pt_u2f(m2.y), pt_u2f(m2.z), pt_u2f(m2.w)};
-                cnt.inst();
-                pt_ray_ctx(&r, pt_xform_point(w2o, world.o), pt_xform_vec(w2o, world.d));
-                node_base = m6.x; tri_base = m6.y; cur_inst = m6.w; cur_iidx = tg.x + k;   // m6 = node_base, tri_base, mesh_id, inst_id
-                in_blas = true;
-                ng.x = 0; ng.y = 0x80000000u;
-                tg.x = 0; tg.y = 0;
-            }
-        }
-        if (!(ng.y & 0xff000000u)) {
-            for (;;) {
-                if (sp == 0) return true;
-                ng = stack[--sp];
-                if (TWO_LEVEL && ng.x == PT_NONE && ng.y == 0) {   // leaving an instance
-                    r = world; in_blas = false; node_base = 0; tri_base = 0; cur_inst = PT_NONE;
-                    continue;
-                }
-                break;
-            }
+            // TLAS leaf: enter the instance.  Save the remaining groups, push the return sentinel.
+            if (s->sp + 3 > PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
+            if (s->tg.y) stack[s->sp++] = s->tg;
+            if (s->ng.y & 0xff000000u) stack[s->sp++] = s->ng;
+            PtU2 sentinel; sentinel.x = PT_NONE; sentinel.y = 0; stack[s->sp++] = sentinel;
+            const PtU4* ip = sc.instances + 7 * (size_t)(s->tg.x + k);
+            PtU4 m0 = ip[0], m1 = ip[1], m2 = ip[2], m6 = ip[6];
+            float w2o[12] = {pt_u2f(m0.x), pt_u2f(m0.y), pt_u2f(m0.z), pt_u2f(m0.w), pt_u2f(m1.x), pt_u2f(m1.y),
+                             pt_u2f(m1.z), pt_u2f(m1.w), pt_u2f(m2.x), pt_u2f(m2.y), pt_u2f(m2.z), pt_u2f(m2.w)};
+            cnt.inst();
+            pt_ray_ctx(&s->r, pt_xform_point(w2o, s->world.o), pt_xform_vec(w2o, s->world.d));
+            s->node_base = m6.x; s->tri_base = m6.y; s->cur_inst = m6.w; s->cur_iidx = s->tg.x + k;   // m6 = node_base, tri_base, mesh_id, inst_id
+            s->in_blas = true;
+            s->ng.x = 0; s->ng.y = 0x80000000u;
+            s->tg.x = 0; s->tg.y = 0;
         }
     }
+    if (!(s->ng.y & 0xff000000u)) {
+        for (;;) {
+            if (s->sp == 0) return PT_STEP_DONE;
+            s->ng = stack[--s->sp];
+            if (TWO_LEVEL && s->ng.x == PT_NONE && s->ng.y == 0) {   // leaving an instance
+                s->r = s->world; s->in_blas = false; s->node_base = 0; s->tri_base = 0; s->cur_inst = PT_NONE;
+                continue;
+            }
+            break;
+        }
+    }
+    return PT_STEP_RUNNING;
+}
+
+// Whole traversal of one ray.  Returns false on traversal-stack overflow (reported through the status word).
+template <bool ANY, bool TWO_LEVEL, class Counter>
+PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best, Counter& cnt) {
+    PtTravState s;
+    PtU2 stack[PT_STACK_SIZE];
+    pt_trav_init<TWO_LEVEL>(&s, o, d, tmin, tmax, best);
+    while (pt_trav_step<ANY, TWO_LEVEL>(sc, &s, stack, best, cnt) == PT_STEP_RUNNING) {}
+    return !s.overflow;
 }
