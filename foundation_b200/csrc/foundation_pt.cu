@@ -63,7 +63,7 @@ struct foundation_pt_context {
     foundation_pt_config cfg{};
     foundation_pt_allocator host_alloc{};
     int device = 0, num_sms = 0, trace_blocks_per_sm = 8, fetch_thresh = 24;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // compute, H2D, D2H
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     mutable std::string err = "no error";
 
@@ -392,7 +392,8 @@ int32_t foundation_pt_create(const foundation_pt_config* config, const foundatio
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(ctx->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev2)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev3)) != cudaSuccess) {
         g_create_error = std::string("CUDA init failed: ") + cudaGetErrorString(e);
         delete ctx;
@@ -411,11 +412,12 @@ int32_t foundation_pt_destroy(foundation_pt_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2); if (ctx->ev3) cudaEventDestroy(ctx->ev3);
-    cudaStream_t s1 = ctx->stream, s2 = ctx->stream2;
+    cudaStream_t s1 = ctx->stream, s2 = ctx->stream2, s3 = ctx->stream3;
     delete ctx;   // frees device buffers
-    if (s1) cudaStreamDestroy(s1); if (s2) cudaStreamDestroy(s2);
+    if (s1) cudaStreamDestroy(s1); if (s2) cudaStreamDestroy(s2); if (s3) cudaStreamDestroy(s3);
     return FOUNDATION_PT_OK;
 }
 
@@ -780,11 +782,12 @@ int32_t foundation_pt_trace_closest(foundation_pt_context* ctx, const foundation
         int32_t rc = launch_trace<false>(ctx, ctx->d_rays.as<float4>() + 2 * b, n, ctx->d_hits.as<float4>() + b, ctx->d_hit_inst.as<uint32_t>() + b, nullptr);
         if (rc) return rc;
         PT_CK(cudaEventRecord(done_k, ctx->stream));
-        PT_CK(cudaStreamWaitEvent(ctx->stream2, done_k, 0));
-        PT_CK(cudaMemcpyAsync(out_hits + b, ctx->d_hits.as<float4>() + b, n * 16, cudaMemcpyDeviceToHost, ctx->stream2));
-        if (out_inst) PT_CK(cudaMemcpyAsync(out_inst + b, ctx->d_hit_inst.as<uint32_t>() + b, n * 4, cudaMemcpyDeviceToHost, ctx->stream2));
+        PT_CK(cudaStreamWaitEvent(ctx->stream3, done_k, 0));
+        PT_CK(cudaMemcpyAsync(out_hits + b, ctx->d_hits.as<float4>() + b, n * 16, cudaMemcpyDeviceToHost, ctx->stream3));
+        if (out_inst) PT_CK(cudaMemcpyAsync(out_inst + b, ctx->d_hit_inst.as<uint32_t>() + b, n * 4, cudaMemcpyDeviceToHost, ctx->stream3));
     }
     PT_CK(cudaStreamSynchronize(ctx->stream2));
+    PT_CK(cudaStreamSynchronize(ctx->stream3));
     int32_t rc = end_call(ctx);
     if (rc) return rc;
     return check_status(ctx);

@@ -98,8 +98,14 @@ PT_HD void pt_bsdf_eval(const PtBsdf& b, pt_v3 wo, pt_v3 wi, pt_v3* f, float* pd
     float m = 1.0f - dh, m2 = m * m, m5 = m2 * m2 * m;
     pt_v3 F = pt_mk(pt_fma(1.0f - b.f0.x, m5, b.f0.x), pt_fma(1.0f - b.f0.y, m5, b.f0.y), pt_fma(1.0f - b.f0.z, m5, b.f0.z));
     float sp = pt_div(D * G2, 4.0f * woz * wiz);
-    *f = pt_mk(pt_fma(b.kd.x * PT_INV_PI, 1.0f - F.x, F.x * sp), pt_fma(b.kd.y * PT_INV_PI, 1.0f - F.y, F.y * sp),
-               pt_fma(b.kd.z * PT_INV_PI, 1.0f - F.z, F.z * sp));
+    // diffuse base under the coat: weighted by the energy NOT reflected specularly on the way in and out,
+    // (1 - F(n.wo)) (1 - F(n.wi)) — symmetric in wo, wi (reciprocal) and keeps the two-lobe albedo <= 1 at grazing angles
+    float mo = 1.0f - woz, mo2 = mo * mo, mo5 = mo2 * mo2 * mo;
+    float mi = 1.0f - wiz, mi2 = mi * mi, mi5 = mi2 * mi2 * mi;
+    pt_v3 Td = pt_mk((1.0f - pt_fma(1.0f - b.f0.x, mo5, b.f0.x)) * (1.0f - pt_fma(1.0f - b.f0.x, mi5, b.f0.x)),
+                     (1.0f - pt_fma(1.0f - b.f0.y, mo5, b.f0.y)) * (1.0f - pt_fma(1.0f - b.f0.y, mi5, b.f0.y)),
+                     (1.0f - pt_fma(1.0f - b.f0.z, mo5, b.f0.z)) * (1.0f - pt_fma(1.0f - b.f0.z, mi5, b.f0.z)));
+    *f = pt_mk(pt_fma(b.kd.x * PT_INV_PI, Td.x, F.x * sp), pt_fma(b.kd.y * PT_INV_PI, Td.y, F.y * sp), pt_fma(b.kd.z * PT_INV_PI, Td.z, F.z * sp));
     float pdf_s = pt_div(G1 * D, 4.0f * woz);
     float pdf_d = wiz * PT_INV_PI;
     *pdf = pt_fma(b.p_spec, pdf_s, (1.0f - b.p_spec) * pdf_d);

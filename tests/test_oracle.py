@@ -1,0 +1,255 @@
+"""CPU tier: pins the oracle (known-answer vectors, exhaustive ground truth, independent float64 check, golden
+fixtures) and checks the product's per-item device bodies, executed by the CPU emulation harness, against it."""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from foundation_b200 import scenes
+from oracle import pt_oracle as orc
+from oracle.pt_oracle import HIT_DTYPE, NODE_DTYPE, OracleScene
+from tests.util import SMALL_SCENES, assert_hits_equal, ray_mix
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---------------------------------------------------------------------------------------------- known answers
+def test_pcg32_known_answer_vector():
+    """O'Neill's pcg32 demo (pcg-c-basic, seed 42 / stream 54): the published first six outputs."""
+    want = [0xA15C02B7, 0x7B47F409, 0xBA1D3330, 0x83D2F293, 0xBFA4784B, 0xCBED606E]
+    assert list(orc.pcg_raw(42, 54, 6)) == want
+
+
+def test_pcg_streams_are_distinct_per_pixel_and_sample():
+    a = orc.pcg(1, 10, 0, 8); b = orc.pcg(1, 11, 0, 8); c = orc.pcg(1, 10, 1, 8); d = orc.pcg(2, 10, 0, 8)
+    assert len({a.tobytes(), b.tobytes(), c.tobytes(), d.tobytes()}) == 4
+    assert np.array_equal(a, orc.pcg(1, 10, 0, 8))
+
+
+def test_morton63_is_bit_interleave():
+    rng = np.random.default_rng(0)
+    lo = np.zeros(3, np.float32); inv = np.full(3, 2097152.0, np.float32)       # unit cube -> 21-bit grid
+    L = orc.lib()
+    for _ in range(200):
+        c = rng.random(3).astype(np.float32)
+        q = np.minimum((c * np.float32(2097152.0)).astype(np.uint64), 2097151)
+        want = 0
+        for bit in range(21):
+            for axis in range(3):
+                want |= ((int(q[axis]) >> bit) & 1) << (3 * bit + (2 - axis))
+        got = L.orc_morton(c.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p), inv.ctypes.data_as(C.c_void_p))
+        assert got == want
+
+
+def test_sincos2pi_accuracy():
+    u = np.linspace(0, 1, 4097, endpoint=False, dtype=np.float32)
+    sc = np.asarray([orc.sincos2pi(float(x)) for x in u])
+    assert np.abs(sc[:, 0] - np.sin(2 * np.pi * u.astype(np.float64))).max() < 4e-7
+    assert np.abs(sc[:, 1] - np.cos(2 * np.pi * u.astype(np.float64))).max() < 4e-7
+
+
+# ---------------------------------------------------------------------------------------------- scenes
+def test_scene_triangle_counts_match_baseline_configs():
+    assert scenes.cornell_box().num_triangles == 32
+    assert scenes.sphere_field(num_spheres=3, subdiv=3).num_triangles == 3 * 1280 + 4
+    assert scenes.fractal_terrain(n=50).num_triangles == 2 * 50 * 50 + 2
+    assert 2 * 2236 ** 2 + 2 == 9_999_394                                     # config 3 at full size
+    s = scenes.instanced_patches(num_instances=20, patch=71)
+    assert s.meshes[0].indices.shape[0] == 10082 and s.effective_triangles == 20 * 10082 + 2
+
+
+def test_reference_camera_conventions():
+    """Renderer::Draw's camera (Renderer.cpp:373-380): eye (2,2,2), +Z up, Y flipped: the centre ray points at the origin,
+    pixel row 0 is the top of the image."""
+    view, proj = scenes.reference_camera()
+    o = OracleScene(scenes.cornell_box()); o.camera_set(view, proj)
+    cam = o.camera_get()
+    eye, d0, dx, dy = cam[0:3], cam[3:6], cam[6:9], cam[9:12]
+    assert np.allclose(eye, [2, 2, 2], atol=1e-5)
+    c = d0 / np.linalg.norm(d0)
+    assert np.allclose(c, -np.ones(3) / np.sqrt(3), atol=1e-5)
+    assert dy[2] < 0                      # NDC +y (down the image) moves the ray towards -Z
+    assert abs(np.dot(dx, dy)) < 1e-5 and abs(np.linalg.norm(dx) / np.linalg.norm(dy) - 1920 / 1080) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- traversal ground truth
+@pytest.fixture(scope="module", params=list(SMALL_SCENES))
+def small(request):
+    sc = SMALL_SCENES[request.param]()
+    return request.param, sc, OracleScene(sc)
+
+
+def test_bvh_traversal_equals_exhaustive_search(small):
+    name, sc, o = small
+    rays = ray_mix(sc, 2048)
+    h, i = o.trace_closest(rays)
+    hb, ib = o.trace_closest(rays, brute=True)
+    assert_hits_equal(h, i, hb, ib, name)
+    assert h.tobytes() == hb.tobytes()
+    assert np.array_equal(o.trace_any(rays), o.trace_any(rays, brute=True))
+    assert (h["prim"] != 0xFFFFFFFF).mean() > 0.05
+
+
+def test_hits_agree_with_independent_float64_intersection(small):
+    """Independent of every shared header: numpy float64 Moller-Trumbore of the reported triangle."""
+    name, sc, o = small
+    if sc.instances is not None:
+        pytest.skip("flat scenes only")
+    rays = ray_mix(sc, 1024)
+    h, _ = o.trace_closest(rays)
+    m = sc.meshes[0]
+    hit = h["prim"] != 0xFFFFFFFF
+    tri = m.positions[m.indices[h["prim"][hit]]].astype(np.float64)
+    ro = rays["origin"][hit].astype(np.float64); rd = rays["direction"][hit].astype(np.float64)
+    e1 = tri[:, 1] - tri[:, 0]; e2 = tri[:, 2] - tri[:, 0]
+    p = np.cross(rd, e2); det = (e1 * p).sum(1)
+    tv = ro - tri[:, 0]; q = np.cross(tv, e1)
+    t = (e2 * q).sum(1) / det; u = (tv * p).sum(1) / det; v = (rd * q).sum(1) / det
+    ok = np.abs(det) > 1e-9 * np.linalg.norm(e1, axis=1) * np.linalg.norm(e2, axis=1) * np.linalg.norm(rd, axis=1)
+    assert np.allclose(t[ok], h["t"][hit][ok], rtol=2e-3, atol=1e-4)
+    assert (u[ok] > -1e-3).all() and (v[ok] > -1e-3).all() and (u[ok] + v[ok] < 1 + 1e-3).all()
+    assert np.allclose(u[ok], h["u"][hit][ok], atol=2e-3) and np.allclose(v[ok], h["v"][hit][ok], atol=2e-3)
+
+
+def test_ties_resolve_to_lowest_primitive_index():
+    """Two coincident triangles and a shared edge: the reported id is the smaller one whatever the BVH does."""
+    pos = np.asarray([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], np.float32)
+    idx = np.asarray([[1, 3, 2], [0, 1, 2], [0, 1, 2], [0, 1, 2]], np.uint32)      # prims 1,2,3 coincide; 0 shares the diagonal
+    sc = scenes.Scene("ties", [scenes.Mesh(pos, idx, np.zeros(4, np.uint32))], np.asarray([[.8, .8, .8, .5, 0, 0, 0, 0]], np.float32))
+    o = OracleScene(sc)
+    r = np.zeros(2, scenes.RAY_DTYPE); r["tmax"] = np.inf
+    r["origin"] = [(0.25, 0.25, 1), (0.5, 0.5, 1)]; r["direction"] = [(0, 0, -1), (0, 0, -1)]
+    for brute in (False, True):
+        h, _ = o.trace_closest(r, brute=brute)
+        assert list(h["prim"]) == [1, 0] and list(h["t"]) == [1.0, 1.0]
+
+
+# ---------------------------------------------------------------------------------------------- product bodies under emulation
+def _emu():
+    so = os.path.join(HERE, "emu", "libpt_emu.so")
+    subprocess.run(["make", "-C", os.path.join(HERE, "emu")], check=True, capture_output=True)
+    E = C.CDLL(so)
+    E.emu_build.restype = C.c_uint32
+    return E
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def test_product_build_and_traversal_bodies_match_oracle(small):
+    """pt_build.h (Karras emit, collapse, quantisation) and pt_traverse.h (group-stack traversal) — the code the CUDA
+    kernels run per work item — executed on the CPU: byte-identical BVH8, bit-identical hits, identical visit counters."""
+    name, sc, o = small
+    E = _emu()
+    flat_nodes, flat_tris = [], []
+    for mid, mesh in enumerate(sc.meshes):
+        v = mesh.positions[mesh.indices].astype(np.float32)
+        box = np.ascontiguousarray(np.concatenate([v.min(1), v.max(1)], 1), np.float32)
+        cent = np.ascontiguousarray(((v[:, 0] + v[:, 1]) + v[:, 2]) * np.float32(0.333333343267440796), np.float32)
+        n = len(v)
+        nodes = np.zeros(n + 1, NODE_DTYPE); seq = np.zeros(n, np.uint32); order = np.zeros(n, np.uint32)
+        lo = np.zeros(3, np.float32); hi = np.zeros(3, np.float32)
+        nn = E.emu_build(_p(box), _p(cent), C.c_uint32(n), C.c_uint32(3), _p(lo), _p(hi), _p(nodes), _p(seq), _p(order))
+        on, ot, oo = o.blas(mid)
+        assert nn == len(on) and nodes[:nn].tobytes() == on.tobytes(), f"{name} mesh {mid}: nodes differ"
+        assert np.array_equal(order, oo) and np.array_equal(ot["prim"], order[seq])
+        flat_nodes.append(on); flat_tris.append(ot)
+    rays = ray_mix(sc, 2048)
+    if sc.instances is None:
+        nodes, tris, inst, two = flat_nodes[0], flat_tris[0], None, 0
+    else:
+        tn, _, rec = o.tlas()
+        nodes = np.concatenate([tn] + flat_nodes); tris = np.concatenate(flat_tris); inst = rec; two = 1
+    h, i, cnt = o.trace_closest(rays, counters=True, threads=1)
+    hits = np.zeros(len(rays), HIT_DTYPE); ins = np.zeros(len(rays), np.uint32); c2 = np.zeros(3, np.uint64)
+    ok = E.emu_trace(_p(nodes), _p(tris), _p(inst), two, _p(rays), C.c_uint64(len(rays)), _p(hits), _p(ins), None, 0, _p(c2))
+    assert ok == 1 and hits.tobytes() == h.tobytes() and np.array_equal(ins, i)
+    assert np.array_equal(cnt, c2), f"{name}: visit counters differ {cnt} vs {c2}"
+    occ = np.zeros(len(rays), np.uint8)
+    E.emu_trace(_p(nodes), _p(tris), _p(inst), two, _p(rays), C.c_uint64(len(rays)), None, None, _p(occ), 1, None)
+    assert np.array_equal(occ, o.trace_any(rays))
+
+
+# ---------------------------------------------------------------------------------------------- shading model self-checks
+MATS = [[0.8, 0.8, 0.8, 1.0, 0, 0, 0, 0.0], [1.0, 1.0, 1.0, 0.3, 0, 0, 0, 0.0], [1.0, 1.0, 1.0, 0.5, 0, 0, 0, 1.0], [0.9, 0.6, 0.3, 0.15, 0, 0, 0, 1.0]]
+
+
+@pytest.mark.parametrize("mat", MATS)
+def test_bsdf_reciprocity_energy_and_pdf(mat):
+    rng = np.random.default_rng(5)
+
+    def hemi(n):
+        z = rng.random(n); phi = rng.random(n) * 2 * np.pi; r = np.sqrt(1 - z * z)
+        return np.stack([r * np.cos(phi), r * np.sin(phi), z], 1).astype(np.float32)
+
+    for wo in hemi(6):
+        if wo[2] < 0.1:
+            continue
+        wis = hemi(4000)
+        pdf_int = 0.0
+        for k, wi in enumerate(wis):
+            f1, p1 = orc.bsdf_eval(mat, wo, wi)
+            if k < 300:
+                f2, _ = orc.bsdf_eval(mat, wi, wo)
+                assert np.allclose(f1, f2, rtol=2e-4, atol=1e-6)              # Helmholtz reciprocity
+            pdf_int += p1 * 2 * np.pi / len(wis)
+        # the mixture pdf integrates to <= 1 over the upper hemisphere (VNDF samples below the horizon are rejected);
+        # uniform-hemisphere Monte Carlo of a peaked lobe is noisy, so this only catches gross normalisation errors
+        if mat[3] >= 0.3:                                                     # sharper lobes need far more uniform samples than is worth it here
+            assert 0.55 < pdf_int < 1.2, pdf_int
+        est = []
+        for _ in range(3000):                                                  # albedo via the model's own importance sampling
+            ok, wi = orc.bsdf_sample(mat, wo, float(rng.random()), float(rng.random()), float(rng.random()))
+            if not ok:
+                est.append(0.0); continue
+            f, p = orc.bsdf_eval(mat, wo, wi)
+            est.append(float(f.max()) * wi[2] / p if p > 0 else 0.0)
+        assert np.mean(est) <= 1.06, f"energy gain: albedo {np.mean(est)}"   # 3000-sample MC estimate, sigma ~0.02
+
+
+def test_nee_and_bsdf_sampling_estimators_agree():
+    """Same expectation from light sampling only and BSDF sampling only (Cornell, low resolution, many samples)."""
+    sc = scenes.cornell_box(24, 24)
+    o = OracleScene(sc)
+    spp = 384
+    nee = o.render(24, 24, 11, 0, spp, 3, flags=4)[..., :3].mean() / spp      # NO_BSDF_EMISSION
+    bsdf = o.render(24, 24, 12, 0, spp, 3, flags=2)[..., :3].mean() / spp     # NO_NEE
+    mis = o.render(24, 24, 13, 0, spp, 3, flags=0)[..., :3].mean() / spp
+    assert abs(nee - mis) / mis < 0.06 and abs(bsdf - mis) / mis < 0.12, (nee, bsdf, mis)
+
+
+def test_render_is_deterministic_and_progressive():
+    sc = scenes.cornell_box(32, 32)
+    o = OracleScene(sc)
+    a = o.render(32, 32, 5, 0, 3, 4)
+    b = o.render(32, 32, 5, 0, 1, 4); b = o.render(32, 32, 5, 1, 2, 4, accum=b)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, o.render(32, 32, 5, 0, 3, 4, threads=1))
+    brute = o.render(32, 32, 5, 0, 3, 4, brute=True)
+    assert np.array_equal(a, brute)                                           # the BVH never changes a path
+
+
+# ---------------------------------------------------------------------------------------------- golden fixtures
+def test_golden_fixtures():
+    """Fixtures committed under tests/golden (generated by tests/golden/make_golden.py from this oracle): a regression pin
+    for the arithmetic contract — the GPU tests compare against the same files."""
+    g = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+    for name, want in g["scenes"].items():
+        sc = SMALL_SCENES[name]()
+        o = OracleScene(sc)
+        nodes, tris, order = o.blas(0)
+        assert hashlib.sha256(nodes.tobytes()).hexdigest() == want["blas0_nodes_sha256"], name
+        rays = ray_mix(sc, 512)
+        h, i = o.trace_closest(rays)
+        assert hashlib.sha256(h.tobytes() + i.tobytes()).hexdigest() == want["hits_sha256"], name
+        img = o.render(sc.width, sc.height, 7, 0, 1, 3, background=sc.background)
+        assert hashlib.sha256(img.tobytes()).hexdigest() == want["image_sha256"], name
+    cornell = np.load(os.path.join(HERE, "golden", "cornell_hits.npz"))
+    sc = SMALL_SCENES["cornell"](); o = OracleScene(sc)
+    h, _ = o.trace_closest(cornell["rays"].view(scenes.RAY_DTYPE).reshape(-1))
+    assert np.array_equal(h["prim"], cornell["prim"]) and np.array_equal(h["t"].view(np.uint32), cornell["t_bits"])
