@@ -448,10 +448,10 @@ __global__ void __launch_bounds__(128) k_trace_brute(PtSceneView sc, const PtIns
         for (uint32_t t0 = 0; t0 < ntris; t0 += 128) {
             __syncthreads();
             uint32_t cntt = min(128u, ntris - t0);
-            for (uint32_t k = threadIdx.x; k < 3 * cntt; k += blockDim.x) tile[k] = sc.tris[3 * (size_t)(tri_base + t0) + k];
+            for (uint32_t k = threadIdx.x; k < 3 * cntt; k += blockDim.x) tile[k] = pt_load4(sc.tris + 3 * (size_t)(tri_base + t0) + k);
             __syncthreads();
             if (valid)
-                for (uint32_t k = 0; k < cntt; ++k) pt_test_tri(tile, k, r, a.w, inst_id, ii, &best, nc);
+                for (uint32_t k = 0; k < cntt; ++k) pt_test_tri_words(tile[3 * k], tile[3 * k + 1], tile[3 * k + 2], k, r, a.w, inst_id, ii, &best, nc);   // shared-memory words
         }
     }
     if (!valid) return;

@@ -24,8 +24,17 @@ PT_HD float pt_fmax(float a, float b) { return __builtin_fmaxf(a, b); }
 #define PT_STACK_SIZE 64
 #define PT_IDIR_CLAMP 9.094947017729282e-13f  // 2^-40
 
-struct PtU4 { uint32_t x, y, z, w; };
-struct PtU2 { uint32_t x, y; };
+struct alignas(16) PtU4 { uint32_t x, y, z, w; };   // 16-byte aligned so node / triangle words move as single 128-bit loads
+struct alignas(8) PtU2 { uint32_t x, y; };
+
+#if defined(__CUDA_ARCH__)
+PT_HD PtU4 pt_load4(const PtU4* p) {   // read-only 128-bit load (LDG.E.128.CONSTANT)
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    PtU4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+}
+#else
+PT_HD PtU4 pt_load4(const PtU4* p) { return *p; }
+#endif
 
 // The whole scene as the traversal sees it.
 struct PtSceneView {
@@ -60,6 +69,7 @@ PT_HD uint32_t pt_node_hits(const PtU4& n0, const PtU4& n1, const PtU4& n2, cons
     float bx = (pt_u2f(n0.x) - r.o.x) * r.idir.x, by = (pt_u2f(n0.y) - r.o.y) * r.idir.y, bz = (pt_u2f(n0.z) - r.o.z) * r.idir.z;
     bool negx = !(r.oct_inv & 4u), negy = !(r.oct_inv & 2u), negz = !(r.oct_inv & 1u);
     uint32_t mask = 0;
+    const uint32_t oct4 = r.oct_inv * 0x01010101u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -70,22 +80,22 @@ PT_HD uint32_t pt_node_hits(const PtU4& n0, const PtU4& n1, const PtU4& n2, cons
         uint32_t nx = negx ? qhx : qlx, fx = negx ? qlx : qhx;
         uint32_t ny = negy ? qhy : qly, fy = negy ? qly : qhy;
         uint32_t nz = negz ? qhz : qlz, fz = negz ? qlz : qhz;
+        // byte-parallel decode of the four meta bytes (no per-child branches): internal children (bits 3 and 4 set) get
+        // their bit position 24 + (slot ^ oct), leaves keep their triangle offset; bits = 1 / unary triangle count
+        uint32_t inner4 = (((meta4 & (meta4 << 1)) & 0x10101010u) >> 4) * 0xffu;
+        uint32_t idx4 = (meta4 ^ (oct4 & inner4)) & 0x1f1f1f1fu;
+        uint32_t bits4 = (meta4 >> 5) & 0x07070707u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int j = 0; j < 4; ++j) {
-            uint32_t meta = pt_byte(meta4, j);
             float tnx = pt_fma((float)pt_byte(nx, j), ax, bx), tfx = pt_fma((float)pt_byte(fx, j), ax, bx);
             float tny = pt_fma((float)pt_byte(ny, j), ay, by), tfy = pt_fma((float)pt_byte(fy, j), ay, by);
             float tnz = pt_fma((float)pt_byte(nz, j), az, bz), tfz = pt_fma((float)pt_byte(fz, j), az, bz);
             float tn = pt_fmax(pt_fmax(tnx, tny), pt_fmax(tnz, tmin));
             float tf = pt_fmin(pt_fmin(tfx, tfy), pt_fmin(tfz, tbest));
-            if (tn <= tf) {
-                uint32_t bits = meta >> 5;
-                uint32_t inner = ((meta & 0x18u) == 0x18u) ? 7u : 0u;   // internal children carry 24 + slot
-                uint32_t idx = (meta & 0x1fu) ^ (r.oct_inv & inner);
-                mask |= bits << idx;
-            }
+            uint32_t sel = (tn <= tf) ? 0xffffffffu : 0u;
+            mask |= (pt_byte(bits4, j) << pt_byte(idx4, j)) & sel;
         }
     }
     return mask;
@@ -97,9 +107,10 @@ struct PtHitRec {
     uint32_t tidx, iidx;  // position of the triangle / instance record in the leaf-ordered device arrays (for shading)
 };
 
+// one ray / triangle test against the current best; a, b, c are the triangle's three 16-byte words
 template <class Counter>
-PT_HD void pt_test_tri(const PtU4* tris, uint32_t tri_index, const PtRayCtx& r, float tmin, uint32_t inst, uint32_t iidx, PtHitRec* best, Counter& cnt) {
-    const PtU4 a = tris[3 * (size_t)tri_index + 0], b = tris[3 * (size_t)tri_index + 1], c = tris[3 * (size_t)tri_index + 2];
+PT_HD void pt_test_tri_words(const PtU4& a, const PtU4& b, const PtU4& c, uint32_t tri_index, const PtRayCtx& r, float tmin, uint32_t inst, uint32_t iidx,
+                             PtHitRec* best, Counter& cnt) {
     cnt.tri();
     float t, U, V, ad;
     if (pt_ray_tri(r.o, r.d, pt_mk(pt_u2f(a.x), pt_u2f(a.y), pt_u2f(a.z)), pt_mk(pt_u2f(b.x), pt_u2f(b.y), pt_u2f(b.z)),
@@ -110,6 +121,11 @@ PT_HD void pt_test_tri(const PtU4* tris, uint32_t tri_index, const PtRayCtx& r, 
             best->tidx = tri_index; best->iidx = iidx;
         }
     }
+}
+template <class Counter>
+PT_HD void pt_test_tri(const PtU4* tris, uint32_t tri_index, const PtRayCtx& r, float tmin, uint32_t inst, uint32_t iidx, PtHitRec* best, Counter& cnt) {
+    const PtU4 a = pt_load4(tris + 3 * (size_t)tri_index), b = pt_load4(tris + 3 * (size_t)tri_index + 1), c = pt_load4(tris + 3 * (size_t)tri_index + 2);
+    pt_test_tri_words(a, b, c, tri_index, r, tmin, inst, iidx, best, cnt);
 }
 
 struct PtNoCount { PT_HDM void node() {} PT_HDM void tri() {} PT_HDM void inst() {} };
@@ -147,27 +163,12 @@ PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax
 }
 
 // ANY = true: occlusion query, finishes as soon as any triangle is hit in (tmin, tmax).
+// One step = ONE action per lane: test one pending triangle (or enter one instance) if the lane has any, otherwise
+// visit one node; then pop if both groups are empty.  Keeping the two phases in one loop iteration lets the lanes
+// of a warp that are in different phases make progress in the same iteration.
 template <bool ANY, bool TWO_LEVEL, class Counter>
 PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHitRec* best, Counter& cnt) {
-    if (s->ng.y & 0xff000000u) {
-        uint32_t bit = 31u - (uint32_t)pt_clz32(s->ng.y);
-        s->ng.y &= ~(1u << bit);
-        uint32_t slot = (bit - 24u) ^ s->r.oct_inv;
-        uint32_t child = s->ng.x + (uint32_t)pt_popc(s->ng.y & 0xffu & ~(0xffffffffu << slot));
-        if (s->ng.y & 0xff000000u) {
-            if (s->sp >= PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
-            stack[s->sp++] = s->ng;
-        }
-        const PtU4* np = sc.nodes + 5 * (size_t)(s->node_base + child);
-        const PtU4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
-        cnt.node();
-        uint32_t hits = pt_node_hits(n0, n1, n2, n3, n4, s->r, s->tmin, best->t);
-        s->ng.x = n1.x; s->ng.y = (hits & 0xff000000u) | (n0.w >> 24);
-        s->tg.x = n1.y; s->tg.y = hits & 0x00ffffffu;
-    } else {
-        s->tg = s->ng; s->ng.x = 0; s->ng.y = 0;
-    }
-    while (s->tg.y) {
+    if (s->tg.y) {
         uint32_t k = (uint32_t)pt_ffs0(s->tg.y);
         s->tg.y &= s->tg.y - 1u;
         if (!TWO_LEVEL || s->in_blas) {
@@ -180,7 +181,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
             if (s->ng.y & 0xff000000u) stack[s->sp++] = s->ng;
             PtU2 sentinel; sentinel.x = PT_NONE; sentinel.y = 0; stack[s->sp++] = sentinel;
             const PtU4* ip = sc.instances + 7 * (size_t)(s->tg.x + k);
-            PtU4 m0 = ip[0], m1 = ip[1], m2 = ip[2], m6 = ip[6];
+            PtU4 m0 = pt_load4(ip), m1 = pt_load4(ip + 1), m2 = pt_load4(ip + 2), m6 = pt_load4(ip + 6);
             float w2o[12] = {pt_u2f(m0.x), pt_u2f(m0.y), pt_u2f(m0.z), pt_u2f(m0.w), pt_u2f(m1.x), pt_u2f(m1.y),
                              pt_u2f(m1.z), pt_u2f(m1.w), pt_u2f(m2.x), pt_u2f(m2.y), pt_u2f(m2.z), pt_u2f(m2.w)};
             cnt.inst();
@@ -190,17 +191,31 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
             s->ng.x = 0; s->ng.y = 0x80000000u;
             s->tg.x = 0; s->tg.y = 0;
         }
-    }
-    if (!(s->ng.y & 0xff000000u)) {
-        for (;;) {
-            if (s->sp == 0) return PT_STEP_DONE;
-            s->ng = stack[--s->sp];
-            if (TWO_LEVEL && s->ng.x == PT_NONE && s->ng.y == 0) {   // leaving an instance
-                s->r = s->world; s->in_blas = false; s->node_base = 0; s->tri_base = 0; s->cur_inst = PT_NONE;
-                continue;
-            }
-            break;
+    } else if (s->ng.y & 0xff000000u) {
+        uint32_t bit = 31u - (uint32_t)pt_clz32(s->ng.y);
+        s->ng.y &= ~(1u << bit);
+        uint32_t slot = (bit - 24u) ^ s->r.oct_inv;
+        uint32_t child = s->ng.x + (uint32_t)pt_popc(s->ng.y & 0xffu & ~(0xffffffffu << slot));
+        if (s->ng.y & 0xff000000u) {
+            if (s->sp >= PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
+            stack[s->sp++] = s->ng;
         }
+        const PtU4* np = sc.nodes + 5 * (size_t)(s->node_base + child);
+        const PtU4 n0 = pt_load4(np), n1 = pt_load4(np + 1), n2 = pt_load4(np + 2), n3 = pt_load4(np + 3), n4 = pt_load4(np + 4);
+        cnt.node();
+        uint32_t hits = pt_node_hits(n0, n1, n2, n3, n4, s->r, s->tmin, best->t);
+        s->ng.x = n1.x; s->ng.y = (hits & 0xff000000u) | (n0.w >> 24);
+        s->tg.x = n1.y; s->tg.y = hits & 0x00ffffffu;
+    }
+    // both groups empty: pop the next group (a node group keeps its hit bits in the top byte, a triangle group has none)
+    while (!s->tg.y && !(s->ng.y & 0xff000000u)) {
+        if (s->sp == 0) return PT_STEP_DONE;
+        PtU2 e = stack[--s->sp];
+        if (TWO_LEVEL && e.x == PT_NONE && e.y == 0) {   // leaving an instance
+            s->r = s->world; s->in_blas = false; s->node_base = 0; s->tri_base = 0; s->cur_inst = PT_NONE;
+            continue;
+        }
+        if (e.y & 0xff000000u) s->ng = e; else { s->tg = e; s->ng.x = 0; s->ng.y = 0; }
     }
     return PT_STEP_RUNNING;
 }
