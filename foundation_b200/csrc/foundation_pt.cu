@@ -36,9 +36,32 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// std allocator over the caller's host-allocation callbacks (foundation_pt_allocator; NULL callbacks = malloc/free):
+// every host-side copy of scene data the context keeps goes through it, like the reference threads Core::Allocator
+// through its containers (src/Core/Allocator/StlContainers.hpp:11-66).
+template <class T>
+struct CbAlloc {
+    using value_type = T;
+    const foundation_pt_allocator* cb = nullptr;
+    CbAlloc() = default;
+    explicit CbAlloc(const foundation_pt_allocator* c) : cb(c) {}
+    template <class U> CbAlloc(const CbAlloc<U>& o) : cb(o.cb) {}
+    T* allocate(size_t n) {
+        void* p = (cb && cb->alloc) ? cb->alloc(cb->user, n * sizeof(T), alignof(T) < 16 ? 16 : alignof(T)) : std::malloc(n * sizeof(T));
+        if (!p) throw std::bad_alloc();
+        return static_cast<T*>(p);
+    }
+    void deallocate(T* p, size_t) { if (cb && cb->free) cb->free(cb->user, p); else std::free(p); }
+    template <class U> bool operator==(const CbAlloc<U>& o) const { return cb == o.cb; }
+    template <class U> bool operator!=(const CbAlloc<U>& o) const { return cb != o.cb; }
+};
+template <class T> using HostVec = std::vector<T, CbAlloc<T>>;
+
 struct Mesh {
-    // host copies (light extraction, validation)
-    std::vector<uint8_t> h_pos; std::vector<uint8_t> h_idx; std::vector<uint32_t> h_mat;
+    // host copies (light extraction, validation), allocated through the caller's allocator
+    HostVec<uint8_t> h_pos; HostVec<uint8_t> h_idx; HostVec<uint32_t> h_mat;
+    explicit Mesh(const foundation_pt_allocator* cb) : h_pos(CbAlloc<uint8_t>(cb)), h_idx(CbAlloc<uint8_t>(cb)), h_mat(CbAlloc<uint32_t>(cb)) {}
+    Mesh(Mesh&&) = default; Mesh& operator=(Mesh&&) = default;
     uint32_t stride = 0, idx_fmt = 0, nverts = 0, ntris = 0;
     DevBuf d_pos, d_idx, d_mat;
     // build products
@@ -284,7 +307,7 @@ int32_t end_call(Ctx* ctx) {
 int32_t setup_wave(Ctx* ctx) {
     if (ctx->wave_ready) return 0;
     uint32_t W = ctx->cfg.width, H = ctx->cfg.height;
-    std::vector<uint32_t> slot_pixel;
+    HostVec<uint32_t> slot_pixel{CbAlloc<uint32_t>(ctx->host_alloc.alloc ? &ctx->host_alloc : nullptr)};
     bool whole = ctx->part_count <= 1;
     if (!whole) {
         uint32_t T = ctx->part_tile ? ctx->part_tile : 32;
@@ -444,7 +467,7 @@ int32_t foundation_pt_mesh_create(foundation_pt_context* ctx, const void* positi
     if (num_triangles > 0x7fffffffu / 3) return ctx->fail(FOUNDATION_PT_ERR_UNSUPPORTED, "mesh_create: too many triangles in one mesh");
     PT_TRY
     cudaSetDevice(ctx->device);
-    Mesh m;
+    Mesh m(ctx->host_alloc.alloc ? &ctx->host_alloc : nullptr);
     m.stride = (uint32_t)pos_stride_bytes; m.idx_fmt = index_format; m.nverts = num_vertices; m.ntris = num_triangles;
     size_t pos_bytes = (size_t)(num_vertices - 1) * pos_stride_bytes + 12;
     m.h_pos.assign((const uint8_t*)positions, (const uint8_t*)positions + pos_bytes);
@@ -575,7 +598,7 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
         ctx->view.nodes = m.d_nodes.as<PtU4>(); ctx->view.tris = m.d_tris.as<PtU4>(); ctx->view.instances = nullptr;
     }
     // lights (host; emissive triangles are few) — instance order, then input triangle order
-    std::vector<PtLight> lights;
+    HostVec<PtLight> lights{CbAlloc<PtLight>(ctx->host_alloc.alloc ? &ctx->host_alloc : nullptr)};
     auto emissive = [&](uint32_t mid) -> const PtMaterial* {
         const PtMaterial& mt = ctx->mats[mid < ctx->mats.size() ? mid : 0];
         return (mt.er > 0 || mt.eg > 0 || mt.eb > 0) ? &mt : nullptr;

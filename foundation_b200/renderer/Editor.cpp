@@ -1,0 +1,80 @@
+// Editor.cpp — headless stand-in for the reference's only caller of the renderer (src/Editor/Editor.cpp:13-44):
+// construct the allocator, the device handle and the Renderer, call Draw() in a loop, report allocator bytes at exit.
+// There is no window on the GPU box, so the loop runs a fixed number of frames and writes the result to disk instead of presenting.
+//   usage: foundation_editor <scene.fpts> <frames> <samples_per_draw> <max_bounces> [out.pfm] [out.ppm]
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "Renderer.hpp"
+
+using namespace Foundation;
+
+namespace {
+// counting heap allocator, the role of HeapAllocatorMultiThreaded (src/Core/Allocator/HeapAllocator.hpp:9-70)
+class CountingAllocator final : public Core::Allocator {
+    std::atomic<size_t> m_used{0};
+    struct Header { size_t size; void* base; };
+public:
+    pointer Allocate(size_type size) override { return Allocate(size, alignof(std::max_align_t)); }
+    pointer Allocate(size_type size, size_t alignment) override {
+        if (alignment < alignof(Header)) alignment = alignof(Header);
+        void* base = std::malloc(size + alignment + sizeof(Header));
+        if (!base) return nullptr;
+        uintptr_t p = (reinterpret_cast<uintptr_t>(base) + sizeof(Header) + alignment - 1) & ~(uintptr_t)(alignment - 1);
+        Header* h = reinterpret_cast<Header*>(p) - 1; h->size = size; h->base = base;
+        m_used += size;
+        return reinterpret_cast<void*>(p);
+    }
+    void Deallocate(pointer ptr, size_type) override { Deallocate(ptr); }
+    void Deallocate(pointer ptr) override {
+        if (!ptr) return;
+        Header* h = reinterpret_cast<Header*>(ptr) - 1;
+        m_used -= h->size; std::free(h->base);
+    }
+    pointer Reallocate(pointer ptr, size_type new_size, size_t alignment) override {
+        pointer n = Allocate(new_size, alignment);
+        if (ptr && n) { Header* h = reinterpret_cast<Header*>(ptr) - 1; std::memcpy(n, ptr, h->size < new_size ? h->size : new_size); Deallocate(ptr); }
+        return n;
+    }
+    size_type GetUsedMemory() const noexcept override { return m_used.load(); }
+};
+CountingAllocator g_Allocator;
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 5) { std::fprintf(stderr, "usage: %s scene.fpts frames samples_per_draw max_bounces [out.pfm] [out.ppm]\n", argv[0]); return 2; }
+    Renderer::SceneDesc scene; std::string err;
+    if (!scene.Load(argv[1], &err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 2; }
+    int frames = std::atoi(argv[2]); uint32_t spd = (uint32_t)std::atoi(argv[3]), bounces = (uint32_t)std::atoi(argv[4]);
+    {
+        Renderer::DeviceHandle device{0};                       // the reference takes EnumerateDevices()[0] (Editor.cpp:18)
+        Renderer::Renderer renderer(device, g_Allocator.Ptr(), scene, /*seed*/ 7);
+        renderer.SetQuality(spd, bounces);
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < frames; ++i) renderer.Draw();       // Main Loop (Editor.cpp:20-23)
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        foundation_pt_build_stats bs = renderer.BuildStats();
+        std::printf("frames=%d spp=%u ms=%.3f spp_per_s=%.2f tris=%llu nodes8=%llu build_ms=%.2f\n", frames, renderer.SamplesDone(), ms,
+                    renderer.SamplesDone() / (ms * 1e-3), (unsigned long long)bs.num_triangles, (unsigned long long)bs.num_nodes8, bs.build_ms);
+        if (argc > 5) {   // linear radiance sum (PFM is bottom-up: write rows reversed), plus the sample count in the alpha of the raw dump
+            std::vector<float> acc; renderer.ReadAccum(&acc);
+            FILE* f = std::fopen(argv[5], "wb");
+            if (f) { std::fwrite(acc.data(), sizeof(float), acc.size(), f); std::fclose(f); }   // raw float4 dump (row-major from the top-left)
+        }
+        if (argc > 6) {
+            FILE* f = std::fopen(argv[6], "wb");
+            if (f) {
+                std::fprintf(f, "P6\n%u %u\n255\n", renderer.Width(), renderer.Height());
+                const uint8_t* img = renderer.PresentImage();
+                for (size_t p = 0; p < (size_t)renderer.Width() * renderer.Height(); ++p) std::fwrite(img + 4 * p, 1, 3, f);
+                std::fclose(f);
+            }
+        }
+    }
+    std::printf("Quitting. Memory Used: %zu bytes\n", g_Allocator.GetUsedMemory());   // Editor.cpp:25
+    return 0;
+}

@@ -374,5 +374,21 @@ def stress_rays(scene: Scene, count: int, seed: int = 11) -> np.ndarray:
     return rays
 
 
+def save_scene(scene: Scene, path: str) -> None:
+    """Writes the "FPTS" container read by the C++ host (foundation_b200/renderer/Renderer.cpp SceneDesc::Load):
+    header 8 x u32 {magic 'FPTS', version 1, width, height, meshes, materials, instances, 0}, view, proj, background, materials
+    (8 x f32 each), instances (64 B each), then per mesh {nverts, ntris, positions f32x3, indices u32x3, material ids u32}."""
+    inst = scene.instances if scene.instances is not None else np.zeros(0, INSTANCE_DTYPE)
+    with open(path, "wb") as f:
+        f.write(np.asarray([0x53545046, 1, scene.width, scene.height, len(scene.meshes), scene.materials.shape[0], len(inst), 0], np.uint32).tobytes())
+        f.write(np.ascontiguousarray(scene.view, np.float32).tobytes()); f.write(np.ascontiguousarray(scene.proj, np.float32).tobytes())
+        f.write(np.asarray(scene.background, np.float32).tobytes())
+        f.write(np.ascontiguousarray(scene.materials, np.float32).tobytes()); f.write(np.ascontiguousarray(inst).tobytes())
+        for m in scene.meshes:
+            f.write(np.asarray([m.positions.shape[0], m.indices.shape[0]], np.uint32).tobytes())
+            f.write(np.ascontiguousarray(m.positions, np.float32).tobytes()); f.write(np.ascontiguousarray(m.indices, np.uint32).tobytes())
+            f.write(np.ascontiguousarray(m.material_ids, np.uint32).tobytes())
+
+
 def by_name(name: str, **kw) -> Scene:
     return {"cornell": cornell_box, "spheres": sphere_field, "terrain": fractal_terrain, "instanced": instanced_patches}[name](**kw)

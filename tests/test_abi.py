@@ -69,3 +69,17 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".h", ".cuh", ".cu", ".cpp", ".hpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r'(#include\s*"[^"]*oracle/|from\s+oracle|import\s+oracle|libpt_oracle|pt_emu)', txt), os.path.join(dirpath, f)
+
+
+def test_cpp_renderer_host_links_against_the_c_abi_only():
+    """The Foundation-shaped C++ host (Renderer(device, allocator) / Draw()) compiles with g++ alone and links only
+    libfoundation_pt.so — no CUDA headers, no torch."""
+    rdir = os.path.join(ROOT, "foundation_b200", "renderer")
+    subprocess.run(["make", "-C", rdir, "-B"], check=True, capture_output=True)
+    exe = os.path.join(rdir, "foundation_editor")
+    assert os.path.exists(exe)
+    needed = subprocess.run(["readelf", "-d", exe], capture_output=True, text=True).stdout
+    assert "libfoundation_pt.so" in needed and "libcuda" not in needed and "libtorch" not in needed
+    for f in ("Renderer.hpp", "Renderer.cpp", "Editor.cpp"):
+        txt = open(os.path.join(rdir, f)).read()
+        assert "cuda_runtime" not in txt and "torch" not in txt.replace("no torch", "")
