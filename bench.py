@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--terrain-n", type=int, default=2236)
     ap.add_argument("--log2-rays", type=int, default=26)
-    ap.add_argument("--spp", type=int, default=4, help="samples per pixel per render step of the spp/s measurement (0 = skip)")
+    ap.add_argument("--spp", type=int, default=8, help="samples per pixel per render step of the spp/s measurement (0 = skip)")
     ap.add_argument("--bounces", type=int, default=8)
     ap.add_argument("--cpu-log2-rays", type=int, default=22, help="bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -238,14 +238,17 @@ def main():
         render_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         spp_per_s = a.spp / (render_ms * 1e-3)
         rst = tr.stats()
-        if rank == 0 and frame is not None:
-            frame_mean = float(frame[..., :3].mean().item() / (a.spp + 1))
+        if rank == 0:
+            fr = frame.cpu().numpy() if frame is not None else tr.read_accum()
+            frame_mean = float(fr[..., :3].mean() / (a.spp + 1))
         render_rays = sum_over_ranks(float(rst.rays_extend + rst.rays_shadow))
     else:
         render_rays = 0.0
 
     if rank != 0:
         barrier()
+        if dist:
+            dist.destroy_process_group()
         return
 
     # ---- parity gate + CPU baseline + roofline inputs (rank 0, host cores) ----
@@ -294,6 +297,8 @@ def main():
                       "mtris_per_s": bs.num_triangles / (bs.build_ms * 1e-3) / 1e6}}
     print(json.dumps(line), flush=True)
     barrier()
+    if dist:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -110,7 +110,8 @@ struct foundation_pt_context {
     uint32_t part_rank = 0, part_count = 1, part_tile = 32;
     bool wave_ready = false;
     DevBuf w_ray_o, w_ray_d, w_beta, w_L, w_rng, w_hit, w_active, w_next, w_sorted, w_sh_o, w_sh_d, w_sh_c, w_slot_pixel, w_ctr, w_keyhist, d_accum;
-    uint32_t num_slots = 0;
+    uint32_t num_slots = 0;      // owned pixels
+    uint32_t wave_samples = 1;   // samples of every owned pixel traced together in one wave
     DevBuf d_status, d_counters;
 
     // explicit ray set
@@ -319,7 +320,12 @@ int32_t setup_wave(Ctx* ctx) {
         PT_CK(cudaMemcpyAsync(ctx->w_slot_pixel.p, slot_pixel.data(), (size_t)ctx->num_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
         PT_CK(cudaStreamSynchronize(ctx->stream));
     } else { ctx->num_slots = W * H; ctx->w_slot_pixel.release(); }
-    size_t S = ctx->num_slots ? ctx->num_slots : 1;
+    // several samples per wave: more rays in flight per launch and fewer launches per sample (results unchanged: one slot per
+    // (pixel, sample), accumulated in sample order).  Capped at 8 samples / 16 M slots.
+    ctx->wave_samples = 1;
+    if (ctx->num_slots) { uint64_t k = (16ull << 20) / ctx->num_slots; ctx->wave_samples = (uint32_t)(k < 1 ? 1 : (k > 8 ? 8 : k)); }
+    if (const char* e = getenv("FOUNDATION_PT_WAVE_SAMPLES")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->wave_samples = v; }
+    size_t S = (size_t)(ctx->num_slots ? ctx->num_slots : 1) * ctx->wave_samples;
     PT_CK(ctx->w_ray_o.alloc(S * 16)); PT_CK(ctx->w_ray_d.alloc(S * 16)); PT_CK(ctx->w_beta.alloc(S * 16)); PT_CK(ctx->w_L.alloc(S * 16));
     PT_CK(ctx->w_rng.alloc(S * 16)); PT_CK(ctx->w_hit.alloc(S * 16)); PT_CK(ctx->w_active.alloc(S * 4)); PT_CK(ctx->w_next.alloc(S * 4));
     PT_CK(ctx->w_sorted.alloc(S * 4)); PT_CK(ctx->w_sh_o.alloc(S * 16)); PT_CK(ctx->w_sh_d.alloc(S * 16)); PT_CK(ctx->w_sh_c.alloc(S * 16));
@@ -340,18 +346,21 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
     w.rng = ctx->w_rng.as<uint4>(); w.hit = ctx->w_hit.as<float4>(); w.active = ctx->w_active.as<uint32_t>(); w.next = ctx->w_next.as<uint32_t>();
     w.sorted = ctx->w_sorted.as<uint32_t>(); w.sh_o = ctx->w_sh_o.as<float4>(); w.sh_d = ctx->w_sh_d.as<float4>(); w.sh_c = ctx->w_sh_c.as<float4>();
     w.slot_pixel = ctx->part_count > 1 ? ctx->w_slot_pixel.as<uint32_t>() : nullptr;
-    w.ctr = ctx->w_ctr.as<PtWaveCounters>(); w.key_hist = ctx->w_keyhist.as<uint32_t>(); w.num_slots = ctx->num_slots;
+    w.ctr = ctx->w_ctr.as<PtWaveCounters>(); w.key_hist = ctx->w_keyhist.as<uint32_t>(); w.num_slots = ctx->num_slots; w.num_pixels = ctx->num_slots;
     PtShadeScene ss;
     ss.sv = ctx->view; ss.mats = ctx->d_mats.as<PtMaterial>(); ss.num_mats = (uint32_t)ctx->mats.size();
     ss.sc.lights = ctx->d_lights.as<PtLight>(); ss.sc.num_lights = ctx->num_lights; ss.sc.light_area = ctx->light_area; ss.sc.ray_eps = ctx->ray_eps;
     ss.sc.flags = ctx->cfg.flags; ss.sc.max_bounces = max_bounces;
     ss.sc.bg[0] = ctx->cfg.background[0]; ss.sc.bg[1] = ctx->cfg.background[1]; ss.sc.bg[2] = ctx->cfg.background[2];
     const bool sort = !(ctx->cfg.flags & FOUNDATION_PT_FLAG_NO_MATERIAL_SORT);
-    const uint32_t S = ctx->num_slots;
-    const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8), gtrace = grid_for(ctx, S, 128, ctx->trace_blocks_per_sm);
     uint32_t* status = ctx->d_status.as<uint32_t>();
-    for (uint32_t smp = s0; smp < s0 + ns; ++smp) {
+    for (uint32_t smp = s0; smp < s0 + ns;) {
+        const uint32_t batch = (s0 + ns - smp) < ctx->wave_samples ? (s0 + ns - smp) : ctx->wave_samples;
+        const uint32_t S = ctx->num_slots * batch;
+        w.num_slots = S;
+        const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8), gtrace = grid_for(ctx, S, 128, ctx->trace_blocks_per_sm);
         PtFrame f; f.cam = ctx->cam; f.seed = ctx->cfg.seed; f.width = ctx->cfg.width; f.height = ctx->cfg.height; f.sample = smp;
+        smp += batch;
         w.active = ctx->w_active.as<uint32_t>(); w.next = ctx->w_next.as<uint32_t>();
         PT_LAUNCH(ctx, k_raygen, g256, 256, w, f);
         for (uint32_t b = 0; b <= max_bounces; ++b) {
@@ -369,7 +378,7 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
             PT_LAUNCH(ctx, k_bounce_end, 1, 32, w);
             std::swap(w.active, w.next);
         }
-        PT_LAUNCH(ctx, k_accumulate, g256, 256, w, ctx->d_accum.as<float4>());
+        PT_LAUNCH(ctx, k_accumulate, grid_for(ctx, ctx->num_slots, 256, 8), 256, w, ctx->d_accum.as<float4>());
     }
     PT_CK(cudaGetLastError());
     return 0;
