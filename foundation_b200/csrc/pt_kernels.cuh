@@ -353,6 +353,8 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
     bool active = false, drained = false;   // drained: the global queue is empty (warp-uniform once set)
     unsigned long long idx = 0;
     const uint32_t lane = pt_lane();
+    const bool prefetch = (fetch_thresh >> 8) & 1;   // tuning bits ride in the upper byte of the threshold argument
+    fetch_thresh &= 0xff;
     for (;;) {
         uint32_t need = __ballot_sync(PT_FULL, !active);
         if (need && !drained) {
@@ -374,7 +376,7 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
         }
         if (!__any_sync(PT_FULL, active)) break;
         while (active) {
-            if (pt_trav_step<ANY, TWO_LEVEL>(sc, &st, stack, &best, cnt) == PT_STEP_DONE) {
+            if (pt_trav_step<ANY, TWO_LEVEL>(sc, &st, stack, &best, cnt, prefetch) == PT_STEP_DONE) {
                 if (st.overflow) atomicOr(status, 1u);
                 job.store(idx, best);
                 active = false;
@@ -391,7 +393,7 @@ template <bool ANY>
 struct PtRaySetJob {
     const float4* __restrict__ rays; float4* __restrict__ hits; uint32_t* __restrict__ inst_out; uint8_t* __restrict__ occ;
     __device__ __forceinline__ void load(unsigned long long i, pt_v3* o, pt_v3* d, float* tmin, float* tmax) const {
-        float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+        float4 a = __ldcs(rays + 2 * i), b = __ldcs(rays + 2 * i + 1);   // streaming: read once, do not displace BVH nodes from L2
         *o = pt_mk(a.x, a.y, a.z); *d = pt_mk(b.x, b.y, b.z); *tmin = a.w; *tmax = b.w;
     }
     __device__ __forceinline__ void store(unsigned long long i, const PtHitRec& h) const {
@@ -400,8 +402,8 @@ struct PtRaySetJob {
         if (h.prim == PT_NONE) { o.x = __uint_as_float(PT_INF_BITS); o.y = 0.0f; o.z = 0.0f; }
         else { o.x = h.t; o.y = pt_div(h.U, h.ad); o.z = pt_div(h.V, h.ad); }
         o.w = __uint_as_float(h.prim);
-        hits[i] = o;
-        if (inst_out) inst_out[i] = h.inst;
+        __stcs(hits + i, o);                                                  // streaming store (evict-first)
+        if (inst_out) __stcs(inst_out + i, h.inst);
     }
 };
 

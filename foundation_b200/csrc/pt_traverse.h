@@ -162,17 +162,52 @@ PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax
     s->tg.x = 0; s->tg.y = 0;
 }
 
+#if defined(__CUDA_ARCH__)
+PT_HD void pt_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+PT_HD void pt_prefetch(const void*) {}
+#endif
+
 // ANY = true: occlusion query, finishes as soon as any triangle is hit in (tmin, tmax).
-// One step = ONE action per lane: test one pending triangle (or enter one instance) if the lane has any, otherwise
-// visit one node; then pop if both groups are empty.  Keeping the two phases in one loop iteration lets the lanes
-// of a warp that are in different phases make progress in the same iteration.
+// One step = at most one triangle test (or instance entry) followed, if the lane then has no triangle left, by at most one
+// node visit.  A lane whose node produced a single triangle therefore does both in one iteration, lanes with more pending
+// triangles spend extra iterations in the (short) triangle block only; the triangles of a node are always tested before
+// any of its children is visited, so the visit order — and the node / triangle counters — equal the oracle's.
 template <bool ANY, bool TWO_LEVEL, class Counter>
-PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHitRec* best, Counter& cnt) {
-    if (s->tg.y) {
-        uint32_t k = (uint32_t)pt_ffs0(s->tg.y);
+PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHitRec* best, Counter& cnt, bool prefetch = false) {
+    (void)prefetch;
+    const bool do_tri = s->tg.y != 0;
+    const bool leaf_tri = !TWO_LEVEL || s->in_blas;
+    // the node visit of this step happens iff the lane has no triangle left after (at most) one test; whether it does is known
+    // up front, so the triangle's and the node's 128-bit loads are issued TOGETHER and their latencies overlap
+    const bool do_node = (s->ng.y & 0xff000000u) && ((s->tg.y & (s->tg.y - 1u)) == 0u) && (leaf_tri || !do_tri);
+    uint32_t k = 0, tri_index = 0;
+    PtU4 ta, tb, tc, n0, n1, n2, n3, n4;
+    ta.x = ta.y = ta.z = ta.w = 0; tb = ta; tc = ta; n0 = ta; n1 = ta; n2 = ta; n3 = ta; n4 = ta;
+    if (do_tri) {
+        k = (uint32_t)pt_ffs0(s->tg.y);
         s->tg.y &= s->tg.y - 1u;
-        if (!TWO_LEVEL || s->in_blas) {
-            pt_test_tri(sc.tris, s->tri_base + s->tg.x + k, s->r, s->tmin, s->cur_inst, s->cur_iidx, best, cnt);
+        if (leaf_tri) {
+            tri_index = s->tri_base + s->tg.x + k;
+            const PtU4* tp = sc.tris + 3 * (size_t)tri_index;
+            ta = pt_load4(tp); tb = pt_load4(tp + 1); tc = pt_load4(tp + 2);
+        }
+    }
+    if (do_node) {
+        uint32_t bit = 31u - (uint32_t)pt_clz32(s->ng.y);
+        s->ng.y &= ~(1u << bit);
+        uint32_t slot = (bit - 24u) ^ s->r.oct_inv;
+        uint32_t child = s->ng.x + (uint32_t)pt_popc(s->ng.y & 0xffu & ~(0xffffffffu << slot));
+        if (s->ng.y & 0xff000000u) {
+            if (s->sp >= PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
+            stack[s->sp++] = s->ng;
+        }
+        const PtU4* np = sc.nodes + 5 * (size_t)(s->node_base + child);
+        n0 = pt_load4(np); n1 = pt_load4(np + 1); n2 = pt_load4(np + 2); n3 = pt_load4(np + 3); n4 = pt_load4(np + 4);
+    }
+    if (do_tri) {
+        if (leaf_tri) {
+            pt_test_tri_words(ta, tb, tc, tri_index, s->r, s->tmin, s->cur_inst, s->cur_iidx, best, cnt);
             if (ANY && best->prim != PT_NONE) return PT_STEP_DONE;
         } else {
             // TLAS leaf: enter the instance.  Save the remaining groups, push the return sentinel.
@@ -191,17 +226,8 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
             s->ng.x = 0; s->ng.y = 0x80000000u;
             s->tg.x = 0; s->tg.y = 0;
         }
-    } else if (s->ng.y & 0xff000000u) {
-        uint32_t bit = 31u - (uint32_t)pt_clz32(s->ng.y);
-        s->ng.y &= ~(1u << bit);
-        uint32_t slot = (bit - 24u) ^ s->r.oct_inv;
-        uint32_t child = s->ng.x + (uint32_t)pt_popc(s->ng.y & 0xffu & ~(0xffffffffu << slot));
-        if (s->ng.y & 0xff000000u) {
-            if (s->sp >= PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
-            stack[s->sp++] = s->ng;
-        }
-        const PtU4* np = sc.nodes + 5 * (size_t)(s->node_base + child);
-        const PtU4 n0 = pt_load4(np), n1 = pt_load4(np + 1), n2 = pt_load4(np + 2), n3 = pt_load4(np + 3), n4 = pt_load4(np + 4);
+    }
+    if (do_node) {   // children are culled against the best hit INCLUDING the triangle tested just above
         cnt.node();
         uint32_t hits = pt_node_hits(n0, n1, n2, n3, n4, s->r, s->tmin, best->t);
         s->ng.x = n1.x; s->ng.y = (hits & 0xff000000u) | (n0.w >> 24);
