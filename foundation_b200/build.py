@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libfoundation_pt.so")
+LIB_PATH = os.environ.get("FOUNDATION_PT_LIB") or os.path.join(LIB_DIR, "libfoundation_pt.so")   # override: A/B experiments only
 SOURCES = ["foundation_pt.cu"]
 HEADERS = ["pt_math.h", "pt_layout.h", "pt_shading.h", "pt_host_shared.h", "pt_build.h", "pt_traverse.h", "pt_kernels.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17", "-Xcompiler",

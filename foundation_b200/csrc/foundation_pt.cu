@@ -85,7 +85,7 @@ struct Mesh {
 struct foundation_pt_context {
     foundation_pt_config cfg{};
     foundation_pt_allocator host_alloc{};
-    int device = 0, num_sms = 0, trace_blocks_per_sm = 8, fetch_thresh = 24;
+    int device = 0, num_sms = 0, trace_blocks_per_sm = 0 /* 0 = kernel's own: 8 flat, 6 two-level */, fetch_thresh = 24;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // compute, H2D, D2H
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     mutable std::string err = "no error";
@@ -147,6 +147,10 @@ inline uint32_t grid_for(const Ctx* ctx, uint64_t n, uint32_t block, uint32_t bl
     uint64_t cap = (uint64_t)ctx->num_sms * blocks_per_sm;
     if (need < 1) need = 1;
     return (uint32_t)(need < cap ? need : cap);
+}
+
+inline uint32_t trace_blocks(const Ctx* ctx) {   // persistent grid of the traversal kernels: resident CTAs per SM x SMs
+    return ctx->trace_blocks_per_sm ? (uint32_t)ctx->trace_blocks_per_sm : (uint32_t)PT_TRACE_MIN_BLOCKS(ctx->two_level);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,7 +312,7 @@ void pin_nodes_in_l2(Ctx* ctx, size_t node_bytes) {
 template <bool ANY>
 int32_t launch_trace(Ctx* ctx, const float4* rays, uint64_t n, float4* hits, uint32_t* inst, uint8_t* occ) {
     if (n == 0) return 0;
-    uint32_t grid = grid_for(ctx, n, 128, ctx->trace_blocks_per_sm);
+    uint32_t grid = grid_for(ctx, n, 128, trace_blocks(ctx));
     unsigned long long* wc = reinterpret_cast<unsigned long long*>(ctx->d_status.as<uint32_t>() + 2);
     PT_CK(cudaMemsetAsync(wc, 0, 8, ctx->stream));
     if (ctx->two_level) PT_LAUNCH(ctx, (k_trace_rays<ANY, true, false>), grid, 128, ctx->view, rays, (unsigned long long)n, hits, inst, occ, ctx->d_status.as<uint32_t>(), nullptr, wc, ctx->fetch_thresh);
@@ -379,7 +383,7 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
         const uint32_t batch = (s0 + ns - smp) < ctx->wave_samples ? (s0 + ns - smp) : ctx->wave_samples;
         const uint32_t S = ctx->num_slots * batch;
         w.num_slots = S;
-        const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8), gtrace = grid_for(ctx, S, 128, ctx->trace_blocks_per_sm);
+        const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8), gtrace = grid_for(ctx, S, 128, trace_blocks(ctx));
         PtFrame f; f.cam = ctx->cam; f.seed = ctx->cfg.seed; f.width = ctx->cfg.width; f.height = ctx->cfg.height; f.sample = smp;
         smp += batch;
         w.active = ctx->w_active.as<uint32_t>(); w.next = ctx->w_next.as<uint32_t>();

@@ -341,9 +341,10 @@ struct PtDevCounters { unsigned long long nodes, tris, insts; };
 // owns one ray at a time; when fewer than THRESH lanes of the warp are still traversing, the idle lanes claim
 // new work items from a global counter with ONE atomic per warp (ballot + popc + shfl), so a few long rays no
 // longer hold 31 finished lanes hostage.  Job supplies load(i) -> ray and store(i, hit).
-#ifndef PT_FETCH_THRESH
-#define PT_FETCH_THRESH 20
-#endif
+// Resident CTAs per SM the traversal kernels are compiled for.  Flat scenes: 8 x 128 threads x 64 registers = the whole register
+// file (measured: forcing 10 or 12 CTAs spills and is 25-40 % slower).  Two-level kernels carry the world ray as well and need 80
+// registers: 6 CTAs (forcing 64 registers spills and costs 12 %).
+#define PT_TRACE_MIN_BLOCKS(two_level) ((two_level) ? 6 : 8)
 template <bool ANY, bool TWO_LEVEL, class Counter, class Job>
 __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, unsigned long long n, unsigned long long* work_counter, uint32_t* status,
                                               Counter& cnt, int fetch_thresh) {
@@ -408,7 +409,7 @@ struct PtRaySetJob {
 };
 
 template <bool ANY, bool TWO_LEVEL, bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_rays(PtSceneView sc, const float4* __restrict__ rays, unsigned long long n, float4* __restrict__ hits,
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS(TWO_LEVEL)) k_trace_rays(PtSceneView sc, const float4* __restrict__ rays, unsigned long long n, float4* __restrict__ hits,
                                                     uint32_t* __restrict__ inst_out, uint8_t* __restrict__ occ, uint32_t* status, PtDevCounters* counters,
                                                     unsigned long long* work_counter, int fetch_thresh) {
     PtRaySetJob<ANY> job; job.rays = rays; job.hits = hits; job.inst_out = inst_out; job.occ = occ;
@@ -534,7 +535,7 @@ struct PtExtendJob {
     }
 };
 template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(128) k_extend(PtSceneView sc, PtWave w, uint32_t* status, int fetch_thresh) {
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS(TWO_LEVEL)) k_extend(PtSceneView sc, PtWave w, uint32_t* status, int fetch_thresh) {
     PtExtendJob job; job.w = w; job.tris = sc.tris;
     PtNoCount nc;
     pt_warp_trace<false, TWO_LEVEL>(sc, job, (unsigned long long)w.ctr->n_active, &w.ctr->work_extend, status, nc, fetch_thresh);
@@ -677,7 +678,7 @@ struct PtConnectJob {
     }
 };
 template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(128) k_connect(PtSceneView sc, PtWave w, uint32_t* status, int fetch_thresh) {
+__global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS(TWO_LEVEL)) k_connect(PtSceneView sc, PtWave w, uint32_t* status, int fetch_thresh) {
     PtConnectJob job; job.w = w;
     PtNoCount nc;
     pt_warp_trace<true, TWO_LEVEL>(sc, job, (unsigned long long)w.ctr->n_shadow, &w.ctr->work_connect, status, nc, fetch_thresh);
