@@ -15,6 +15,7 @@ ap.add_argument("--rays", type=int, default=1 << 24)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--spp", type=int, default=0)
 ap.add_argument("--bounces", type=int, default=8)
+ap.add_argument("--sort", type=int, default=0, help="pre-sort rays on the host by a Morton key of the origin with this many bits per axis (experiment)")
 a = ap.parse_args()
 t0 = time.time()
 if a.scene == "terrain":
@@ -32,6 +33,16 @@ bs = tr.load(sc)
 print(f"commit wall {time.time() - t0:.2f}s  build_ms={bs.build_ms:.2f} sort_ms={bs.sort_ms:.2f} nodes8={bs.num_nodes8} bytes={bs.device_bytes / 1e6:.1f}MB", flush=True)
 lo, hi = np.asarray(bs.scene_lo[:]), np.asarray(bs.scene_hi[:])
 rays = scenes.incoherent_rays(lo, hi, a.rays)
+if a.sort:
+    b = a.sort
+    q = np.clip(((rays["origin"].astype(np.float64) - lo) / (hi - lo) * (1 << b)).astype(np.int64), 0, (1 << b) - 1)
+    key = np.zeros(len(rays), np.int64)
+    for bit in range(b):
+        for ax in range(3):
+            key |= ((q[:, ax] >> bit) & 1) << (3 * bit + (2 - ax))
+    octant = (rays["direction"][:, 0] < 0).astype(np.int64) * 4 + (rays["direction"][:, 1] < 0) * 2 + (rays["direction"][:, 2] < 0)
+    key = (key << 3) | octant
+    t0 = time.time(); order = np.argsort(key, kind="stable"); rays = rays[order]; print(f"host sort {time.time() - t0:.1f}s", flush=True)
 tr.rays_upload(rays)
 for r in range(a.reps):
     tr.rays_trace_closest()
