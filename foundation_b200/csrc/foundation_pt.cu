@@ -4,6 +4,7 @@
 // the wavefront render loop (the slot of Renderer::Record's pass body, Renderer.cpp:332-351) and the
 // explicit-ray-set interface used for parity and the Mrays/s metric.
 // There is NO CPU fallback: without a CUDA device foundation_pt_create fails with FOUNDATION_PT_ERR_NO_DEVICE.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,16 +25,38 @@ namespace {
 
 thread_local std::string g_create_error = "no error";
 
+// Device allocations.  While g_pool_stream is set (scene_commit) they are stream-ordered (cudaMallocAsync on the context's
+// stream, pool release threshold raised at create) so the ~30 scratch buffers of a build cost microseconds instead of the
+// milliseconds cudaMalloc / cudaFree take each (and cudaFree synchronises the device).
+thread_local cudaStream_t g_pool_stream = nullptr;
 struct DevBuf {
-    void* p = nullptr; size_t bytes = 0;
+    void* p = nullptr; size_t bytes = 0; cudaStream_t owner = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), owner(o.owner) { o.p = nullptr; o.bytes = 0; o.owner = nullptr; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; owner = o.owner; o.p = nullptr; o.bytes = 0; o.owner = nullptr; }
+        return *this;
+    }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-    cudaError_t alloc(size_t n) { release(); if (n == 0) n = 16; cudaError_t e = cudaMalloc(&p, n); if (e == cudaSuccess) bytes = n; else p = nullptr; return e; }
+    void release() {
+        if (p) { if (owner) cudaFreeAsync(p, owner); else cudaFree(p); }
+        p = nullptr; bytes = 0; owner = nullptr;
+    }
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;
+        cudaError_t e;
+        if (g_pool_stream) { e = cudaMallocAsync(&p, n, g_pool_stream); owner = g_pool_stream; }
+        else { e = cudaMalloc(&p, n); owner = nullptr; }
+        if (e == cudaSuccess) bytes = n; else { p = nullptr; owner = nullptr; }
+        return e;
+    }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PoolScope {   // RAII: stream-ordered allocation inside one API call
+    explicit PoolScope(cudaStream_t s) { g_pool_stream = s; }
+    ~PoolScope() { g_pool_stream = nullptr; }
 };
 
 // std allocator over the caller's host-allocation callbacks (foundation_pt_allocator; NULL callbacks = malloc/free):
@@ -102,6 +125,7 @@ struct foundation_pt_context {
     PtSceneView view{};
     uint32_t num_lights = 0; float light_area = 0, ray_eps = 0;
     size_t l2_window_bytes = 0, l2_carve_bytes = 0;
+    bool use_pool = false;
     float wlo[3] = {0, 0, 0}, whi[3] = {0, 0, 0};
     foundation_pt_build_stats bstats{};
 
@@ -457,6 +481,15 @@ int32_t foundation_pt_create(const foundation_pt_config* config, const foundatio
         return FOUNDATION_PT_ERR_CUDA;
     }
     ctx->num_sms = prop.multiProcessorCount;
+    {   // stream-ordered pool for build scratch: keep freed blocks cached instead of returning them to the driver at every sync
+        cudaMemPool_t pool; int supported = 0;
+        if (!getenv("FOUNDATION_PT_NO_POOL") && cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, ctx->device) == cudaSuccess && supported &&
+            cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess) ctx->use_pool = true;
+        }
+        cudaGetLastError();
+    }
     if (const char* e = getenv("FOUNDATION_PT_FETCH_THRESH")) { int v = atoi(e); if (v >= 0 && v <= 32) ctx->fetch_thresh = v; }
     if (const char* e = getenv("FOUNDATION_PT_PREFETCH")) { if (atoi(e)) ctx->fetch_thresh |= 0x100; }
     if (const char* e = getenv("FOUNDATION_PT_TRACE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->trace_blocks_per_sm = v; }
@@ -548,6 +581,7 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
     if (stats && stats->struct_size != sizeof(foundation_pt_build_stats)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "build_stats struct_size mismatch");
     PT_TRY
     cudaSetDevice(ctx->device);
+    PoolScope pool_scope(ctx->use_pool ? ctx->stream : nullptr);
     ctx->call_launches = 0;
     PT_CK(cudaEventRecord(ctx->ev0, ctx->stream));
     float sort_ms = 0;
@@ -632,28 +666,45 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
         ctx->d_nodes_all.release(); ctx->d_tris_all.release(); ctx->d_instances.release();
         ctx->view.nodes = m.d_nodes.as<PtU4>(); ctx->view.tris = m.d_tris.as<PtU4>(); ctx->view.instances = nullptr;
     }
-    // lights (host; emissive triangles are few) — instance order, then input triangle order
+    // lights — instance order, then input triangle order.  The emissive triangles of each mesh are found on the device
+    // (one streaming pass over the material ids); only those few are transformed on the host.
     HostVec<PtLight> lights{CbAlloc<PtLight>(ctx->host_alloc.alloc ? &ctx->host_alloc : nullptr)};
-    auto emissive = [&](uint32_t mid) -> const PtMaterial* {
-        const PtMaterial& mt = ctx->mats[mid < ctx->mats.size() ? mid : 0];
-        return (mt.er > 0 || mt.eg > 0 || mt.eb > 0) ? &mt : nullptr;
-    };
-    auto add_mesh_lights = [&](const Mesh& m, const float* o2w) {
-        for (uint32_t t = 0; t < m.ntris; ++t) {
-            const PtMaterial* mt = emissive(m.h_mat[t]);
-            if (!mt) continue;
-            float v[9]; m.host_tri(t, v);
-            pt_v3 v0 = pt_mk(v[0], v[1], v[2]), e1 = pt_mk(v[3] - v[0], v[4] - v[1], v[5] - v[2]), e2 = pt_mk(v[6] - v[0], v[7] - v[1], v[8] - v[2]);
-            if (o2w) { v0 = pt_xform_point(o2w, v0); e1 = pt_xform_vec(o2w, e1); e2 = pt_xform_vec(o2w, e2); }
-            PtLight l; pt_light_make(&l, v0, e1, e2, mt->er, mt->eg, mt->eb);
-            lights.push_back(l);
-        }
-    };
     bool any_emissive = false;
-    for (auto& mt : ctx->mats) any_emissive |= (mt.er > 0 || mt.eg > 0 || mt.eb > 0);
+    std::vector<uint8_t> mat_em(ctx->mats.size());
+    for (size_t k = 0; k < ctx->mats.size(); ++k) { const PtMaterial& mt = ctx->mats[k]; mat_em[k] = (mt.er > 0 || mt.eg > 0 || mt.eb > 0) ? 1 : 0; any_emissive |= mat_em[k] != 0; }
     if (any_emissive) {
-        if (ctx->two_level) for (uint32_t i = 0; i < ctx->num_inst; ++i) add_mesh_lights(ctx->meshes[rec[i].mesh_id], rec[i].o2w);
-        else add_mesh_lights(ctx->meshes[0], nullptr);
+        DevBuf d_em, d_cnt;
+        PT_CK(d_em.alloc(mat_em.size())); PT_CK(d_cnt.alloc(16));
+        PT_CK(cudaMemcpyAsync(d_em.p, mat_em.data(), mat_em.size(), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<std::vector<uint32_t>> em_tris(ctx->meshes.size());
+        for (size_t k = 0; k < ctx->meshes.size(); ++k) {
+            Mesh& m = ctx->meshes[k];
+            DevBuf d_list; PT_CK(d_list.alloc((size_t)m.ntris * 4));
+            PT_CK(cudaMemsetAsync(d_cnt.p, 0, 4, ctx->stream));
+            PT_LAUNCH(ctx, k_emissive_list, grid_for(ctx, m.ntris, 256, 8), 256, m.d_mat.as<uint32_t>(), m.ntris, d_em.as<uint8_t>(), (uint32_t)mat_em.size(), d_list.as<uint32_t>(),
+                      d_cnt.as<uint32_t>());
+            uint32_t cnt = 0;
+            PT_CK(cudaMemcpyAsync(&cnt, d_cnt.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PT_CK(cudaStreamSynchronize(ctx->stream));
+            em_tris[k].resize(cnt);
+            if (cnt) PT_CK(cudaMemcpyAsync(em_tris[k].data(), d_list.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PT_CK(cudaStreamSynchronize(ctx->stream));
+            std::sort(em_tris[k].begin(), em_tris[k].end());
+        }
+        auto add_mesh_lights = [&](size_t mesh_index, const float* o2w) {
+            const Mesh& m = ctx->meshes[mesh_index];
+            for (uint32_t t : em_tris[mesh_index]) {
+                uint32_t mid = m.h_mat[t];
+                const PtMaterial& mt = ctx->mats[mid < ctx->mats.size() ? mid : 0];
+                float v[9]; m.host_tri(t, v);
+                pt_v3 v0 = pt_mk(v[0], v[1], v[2]), e1 = pt_mk(v[3] - v[0], v[4] - v[1], v[5] - v[2]), e2 = pt_mk(v[6] - v[0], v[7] - v[1], v[8] - v[2]);
+                if (o2w) { v0 = pt_xform_point(o2w, v0); e1 = pt_xform_vec(o2w, e1); e2 = pt_xform_vec(o2w, e2); }
+                PtLight l; pt_light_make(&l, v0, e1, e2, mt.er, mt.eg, mt.eb);
+                lights.push_back(l);
+            }
+        };
+        if (ctx->two_level) for (uint32_t i = 0; i < ctx->num_inst; ++i) add_mesh_lights(rec[i].mesh_id, rec[i].o2w);
+        else add_mesh_lights(0, nullptr);
     }
     ctx->num_lights = (uint32_t)lights.size();
     ctx->light_area = pt_lights_finalize(lights.data(), ctx->num_lights);

@@ -303,6 +303,24 @@ __global__ void __launch_bounds__(256) k_write_tris(PtMeshRaw m, const uint32_t*
     }
 }
 
+// Emissive-triangle list of a mesh (input for the light table): stream the material ids once on the device instead of
+// walking 10 M triangles on the host.  Order is restored by a host sort of the (tiny) result.
+__global__ void __launch_bounds__(256) k_emissive_list(const uint32_t* mat, uint32_t n, const uint8_t* mat_emissive, uint32_t num_mats, uint32_t* out, uint32_t* count) {
+    const uint32_t rounds = (n + pt_gsize() - 1) / pt_gsize();
+    for (uint32_t r = 0; r < rounds; ++r) {
+        uint32_t i = r * pt_gsize() + pt_gtid();
+        bool em = false;
+        if (i < n) { uint32_t m = mat[i]; em = mat_emissive[m < num_mats ? m : 0] != 0; }
+        uint32_t mask = __ballot_sync(PT_FULL, em);
+        if (mask) {
+            uint32_t base = 0;
+            if (pt_lane() == 0) base = atomicAdd(count, (uint32_t)__popc(mask));
+            base = __shfl_sync(PT_FULL, base, 0);
+            if (em) out[base + __popc(mask & ((1u << pt_lane()) - 1u))] = i;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // A6: TLAS inputs — world boxes of instances, and the leaf-ordered instance records
 // ---------------------------------------------------------------------------------------------------
