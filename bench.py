@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--terrain-n", type=int, default=2236)
     ap.add_argument("--log2-rays", type=int, default=26)
-    ap.add_argument("--spp", type=int, default=8, help="samples per pixel per render step of the spp/s measurement (0 = skip)")
+    ap.add_argument("--spp", type=int, default=64, help="samples per pixel per render step of the spp/s measurement (0 = skip)")
     ap.add_argument("--bounces", type=int, default=8)
     ap.add_argument("--cpu-log2-rays", type=int, default=22, help="bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

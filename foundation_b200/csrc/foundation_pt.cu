@@ -372,7 +372,7 @@ int32_t setup_wave(Ctx* ctx) {
     // several samples per wave: more rays in flight per launch and fewer launches per sample (results unchanged: one slot per
     // (pixel, sample), accumulated in sample order).  Capped at 8 samples / 16 M slots.
     ctx->wave_samples = 1;
-    if (ctx->num_slots) { uint64_t k = (16ull << 20) / ctx->num_slots; ctx->wave_samples = (uint32_t)(k < 1 ? 1 : (k > 8 ? 8 : k)); }
+    if (ctx->num_slots) { uint64_t k = (16ull << 20) / ctx->num_slots; ctx->wave_samples = (uint32_t)(k < 1 ? 1 : (k > 64 ? 64 : k)); }
     if (const char* e = getenv("FOUNDATION_PT_WAVE_SAMPLES")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->wave_samples = v; }
     size_t S = (size_t)(ctx->num_slots ? ctx->num_slots : 1) * ctx->wave_samples;
     PT_CK(ctx->w_ray_o.alloc(S * 16)); PT_CK(ctx->w_ray_d.alloc(S * 16)); PT_CK(ctx->w_beta.alloc(S * 16)); PT_CK(ctx->w_L.alloc(S * 16));
