@@ -13,6 +13,7 @@
 #define PT_FLAG_NO_MATERIAL_SORT 1u
 #define PT_FLAG_NO_NEE 2u
 #define PT_FLAG_NO_BSDF_EMISSION 4u
+#define PT_FLAG_MATERIAL_SORT 8u
 
 struct PtShadeConsts {
     const PtLight* lights;
