@@ -372,7 +372,7 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
     bool active = false, drained = false;   // drained: the global queue is empty (warp-uniform once set)
     unsigned long long idx = 0;
     const uint32_t lane = pt_lane();
-    const bool prefetch = (fetch_thresh >> 8) & 1;   // tuning bits ride in the upper byte of the threshold argument
+    const int opts = fetch_thresh >> 8;   // tuning bits ride in the upper bytes of the threshold argument
     fetch_thresh &= 0xff;
     for (;;) {
         uint32_t need = __ballot_sync(PT_FULL, !active);
@@ -395,7 +395,7 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
         }
         if (!__any_sync(PT_FULL, active)) break;
         while (active) {
-            if (pt_trav_step<ANY, TWO_LEVEL>(sc, &st, stack, &best, cnt, prefetch) == PT_STEP_DONE) {
+            if (pt_trav_step<ANY, TWO_LEVEL>(sc, &st, stack, &best, cnt, opts) == PT_STEP_DONE) {
                 if (st.overflow) atomicOr(status, 1u);
                 job.store(idx, best);
                 active = false;

@@ -65,7 +65,13 @@ struct PtMaterial { float r, g, b, roughness, er, eg, eb, metallic; };
 struct PtCamera { float eye[3], d0[3], dx[3], dy[3]; };
 
 #define PT_PAD_REL 1.9073486328125e-06f  // 2^-19: child boxes are padded by this x max |coordinate| before quantisation
-#define PT_MAX_LEAF 3
+#define PT_MAX_LEAF 1   // default triangles per leaf slot (the format allows 3): measured 7-9 % faster than 3 on configs 2-4, 1.9x on Cornell:
+                       // every extra triangle of a leaf is one more random 64-byte DRAM fetch, a tighter box avoids it
+// Ray-dependent slack of the slab test: every plane distance t = q*a + b is widened by PT_SLAB_EPS * (255 |a| + |b|), a bound on
+// the rounding error of that expression (3 ulp of the larger term, x2.7 margin).  The build-time pad covers coordinates near the
+// mesh; this covers rays whose origin is far away compared with the mesh (instanced BLAS in object space, distant cameras), where
+// the error of (p - o) * idir grows with the distance.  2^-21.
+#define PT_SLAB_EPS 4.76837158203125e-07f
 
 // ---- quantisation rules -------------------------------------------------------------------------
 // biased exponent e such that 255 * 2^(e-127) >= extent (smallest such e, clamped to [1,253])

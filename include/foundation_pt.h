@@ -64,7 +64,7 @@ typedef struct foundation_pt_config {
     int32_t device;         /* CUDA device ordinal; the reference takes EnumerateDevices()[0] (Editor.cpp:18) */
     uint32_t width, height; /* render target; reference: swapchain extent 1920x1080 (Renderer.cpp:41)   */
     uint64_t seed;          /* PCG stream seed for the progressive render                                */
-    uint32_t max_leaf_tris; /* 1..3 triangles per BVH8 leaf slot (0 = default 3)                        */
+    uint32_t max_leaf_tris; /* 1..3 triangles per BVH8 leaf slot (0 = default 1)                        */
     uint32_t flags;         /* FOUNDATION_PT_FLAG_*                                                      */
     float background[3];    /* constant environment radiance returned on a miss                          */
     uint32_t reserved;

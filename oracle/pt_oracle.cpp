@@ -219,7 +219,7 @@ struct Scene {
     std::vector<Mesh> meshes;
     std::vector<PtMaterial> mats;
     std::vector<Inst> insts; bool has_insts = false;
-    uint32_t max_leaf = 3;
+    uint32_t max_leaf = PT_MAX_LEAF;
     // TLAS
     std::vector<PtNode8> tnodes; std::vector<PtInstance> tinst; std::vector<uint32_t> torder; Box3 wbounds;
     std::vector<PtLight> lights; float light_area = 0; float ray_eps = 0;
@@ -366,8 +366,9 @@ struct Trav {
         for (int k = 0; k < 3; ++k) {
             float a = pt_u2f((uint32_t)e[k] << 23) * id[k];
             float bb = (p[k] - o[k]) * id[k];
+            float err = pt_fma(pt_abs(a), 255.0f, pt_abs(bb)) * PT_SLAB_EPS;   // ray-dependent slack, same rule as the device (pt_layout.h)
             float qn = (float)(r.neg[k] ? qh[k][slot] : ql[k][slot]), qf = (float)(r.neg[k] ? ql[k][slot] : qh[k][slot]);
-            tnk[k] = pt_fma(qn, a, bb); tfk[k] = pt_fma(qf, a, bb);
+            tnk[k] = pt_fma(qn, a, bb - err); tfk[k] = pt_fma(qf, a, bb + err);
         }
         tn = fmaxf(fmaxf(tnk[0], tnk[1]), fmaxf(tnk[2], tmin));
         tf = fminf(fminf(tfk[0], tfk[1]), fminf(tfk[2], best->t));
@@ -483,7 +484,7 @@ bool owns_pixel(uint32_t x, uint32_t y, uint32_t rank, uint32_t count, uint32_t 
 // =====================================================================================================
 extern "C" {
 
-void* orc_create(uint32_t max_leaf) { Scene* s = new Scene(); s->max_leaf = max_leaf ? max_leaf : 3; s->mats.push_back(PtMaterial{0.8f, 0.8f, 0.8f, 0.5f, 0, 0, 0, 0}); return s; }
+void* orc_create(uint32_t max_leaf) { Scene* s = new Scene(); s->max_leaf = max_leaf ? max_leaf : PT_MAX_LEAF; s->mats.push_back(PtMaterial{0.8f, 0.8f, 0.8f, 0.5f, 0, 0, 0, 0}); return s; }
 void orc_destroy(void* p) { delete (Scene*)p; }
 
 void orc_materials_set(void* p, const float* m, uint32_t n) {

@@ -82,7 +82,7 @@ def _p(a):
 class OracleScene:
     """Same call sequence as foundation_b200.pt.PathTracer so parity tests read alike on both sides."""
 
-    def __init__(self, scene=None, max_leaf: int = 3):
+    def __init__(self, scene=None, max_leaf: int = 0):
         self._L = lib()
         self._h = C.c_void_p(self._L.orc_create(max_leaf))
         self.flat = True

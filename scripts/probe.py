@@ -16,6 +16,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--spp", type=int, default=0)
 ap.add_argument("--bounces", type=int, default=8)
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--leaf", type=int, default=0)
 ap.add_argument("--sort", type=int, default=0, help="pre-sort rays on the host by a Morton key of the origin with this many bits per axis (experiment)")
 a = ap.parse_args()
 t0 = time.time()
@@ -28,7 +29,7 @@ elif a.scene == "instanced":
 else:
     sc = scenes.cornell_box()
 print(f"scene {sc.name}: {sc.num_triangles} tris ({sc.effective_triangles} effective) generated in {time.time() - t0:.1f}s", flush=True)
-tr = pt.PathTracer(sc.width, sc.height, background=sc.background, flags=a.flags)
+tr = pt.PathTracer(sc.width, sc.height, background=sc.background, flags=a.flags, max_leaf_tris=a.leaf)
 t0 = time.time()
 bs = tr.load(sc)
 print(f"commit wall {time.time() - t0:.2f}s  build_ms={bs.build_ms:.2f} sort_ms={bs.sort_ms:.2f} nodes8={bs.num_nodes8} bytes={bs.device_bytes / 1e6:.1f}MB", flush=True)

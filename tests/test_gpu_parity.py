@@ -189,3 +189,31 @@ def test_cpp_renderer_host_draw_loop_matches_oracle(gpu, tmp_path):
     o = OracleScene(sc).render(sc.width, sc.height, 7, 0, 6, 4, background=sc.background)
     assert np.array_equal(acc, o)
     assert os.path.getsize(ppm) > sc.width * sc.height * 3
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 3])
+def test_leaf_sizes_and_far_origins(gpu, leaf):
+    """max_leaf_tris 1..3 build byte-identically to the oracle and give identical hits, including for rays that start ~100 scene
+    radii away (exercises the ray-dependent slab slack in instanced BLAS)."""
+    sc = scenes.instanced_patches(num_instances=60, patch=8, width=64, height=64)
+    lo, hi = scenes.scene_bounds(sc)
+    rng = np.random.default_rng(5)
+    n = 200000
+    c = (lo + hi) / 2; half = (hi - lo) / 2
+    dirs = rng.normal(size=(n, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    org = c + dirs * np.linalg.norm(half) * 100.0
+    tgt = c + (rng.random((n, 3)) * 2 - 1) * half
+    rays = np.zeros(n, scenes.RAY_DTYPE)
+    rays["origin"] = org.astype(np.float32); d = tgt - org; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["direction"] = d.astype(np.float32); rays["tmax"] = np.inf
+    tr = pt.PathTracer(64, 64, max_leaf_tris=leaf); tr.load(sc)
+    orc = OracleScene(sc, max_leaf=leaf)
+    gn, gt, go = tr.blas_download(0); on, ot, oo = orc.blas(0)
+    assert gn.tobytes() == on.tobytes() and gt.tobytes() == ot.tobytes()
+    tr.rays_upload(rays)
+    tr.rays_trace_closest(); gh, gi = tr.rays_download_hits()
+    tr.rays_trace_brute(); bh, bi = tr.rays_download_hits()
+    assert_hits_equal(gh, gi, bh, bi, f"leaf {leaf}: device BVH vs device exhaustive, far origins")
+    oh, oi = orc.trace_closest(rays[:20000])
+    assert gh[:20000].tobytes() == oh.tobytes() and np.array_equal(gi[:20000], oi)
+    tr.close()

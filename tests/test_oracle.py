@@ -144,8 +144,13 @@ def _p(a):
 def test_product_build_and_traversal_bodies_match_oracle(small):
     """pt_build.h (Karras emit, collapse, quantisation) and pt_traverse.h (group-stack traversal) — the code the CUDA
     kernels run per work item — executed on the CPU: byte-identical BVH8, bit-identical hits, identical visit counters."""
-    name, sc, o = small
+    name, sc, _ = small
     E = _emu()
+    for leaf in (1, 3):
+        _check_product_bodies(name, sc, OracleScene(sc, max_leaf=leaf), E, leaf)
+
+
+def _check_product_bodies(name, sc, o, E, leaf):
     flat_nodes, flat_tris = [], []
     for mid, mesh in enumerate(sc.meshes):
         v = mesh.positions[mesh.indices].astype(np.float32)
@@ -154,7 +159,7 @@ def test_product_build_and_traversal_bodies_match_oracle(small):
         n = len(v)
         nodes = np.zeros(n + 1, NODE_DTYPE); seq = np.zeros(n, np.uint32); order = np.zeros(n, np.uint32)
         lo = np.zeros(3, np.float32); hi = np.zeros(3, np.float32)
-        nn = E.emu_build(_p(box), _p(cent), C.c_uint32(n), C.c_uint32(3), _p(lo), _p(hi), _p(nodes), _p(seq), _p(order))
+        nn = E.emu_build(_p(box), _p(cent), C.c_uint32(n), C.c_uint32(leaf), _p(lo), _p(hi), _p(nodes), _p(seq), _p(order))
         on, ot, oo = o.blas(mid)
         assert nn == len(on) and nodes[:nn].tobytes() == on.tobytes(), f"{name} mesh {mid}: nodes differ"
         assert np.array_equal(order, oo) and np.array_equal(ot["prim"], order[seq])
@@ -253,3 +258,23 @@ def test_golden_fixtures():
     sc = SMALL_SCENES["cornell"](); o = OracleScene(sc)
     h, _ = o.trace_closest(cornell["rays"].view(scenes.RAY_DTYPE).reshape(-1))
     assert np.array_equal(h["prim"], cornell["prim"]) and np.array_equal(h["t"].view(np.uint32), cornell["t_bits"])
+
+
+def test_far_ray_origins_stay_conservative():
+    """Rays starting ~100 scene radii away (instanced BLAS see them in object space, where the mesh is tiny compared with the
+    distance): the ray-dependent slab slack (PT_SLAB_EPS) keeps BVH culling consistent with exhaustive search."""
+    sc = scenes.instanced_patches(num_instances=60, patch=8, width=64, height=64)
+    lo, hi = scenes.scene_bounds(sc)
+    rng = np.random.default_rng(5)
+    n = 30000
+    c = (lo + hi) / 2; half = (hi - lo) / 2
+    dirs = rng.normal(size=(n, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    org = c + dirs * np.linalg.norm(half) * 100.0
+    tgt = c + (rng.random((n, 3)) * 2 - 1) * half
+    rays = np.zeros(n, scenes.RAY_DTYPE)
+    rays["origin"] = org.astype(np.float32); d = tgt - org; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["direction"] = d.astype(np.float32); rays["tmax"] = np.inf
+    for leaf in (1, 3):
+        o = OracleScene(sc, max_leaf=leaf)
+        h, i = o.trace_closest(rays); hb, ib = o.trace_closest(rays, brute=True)
+        assert_hits_equal(h, i, hb, ib, f"far origins, leaf {leaf}")
