@@ -185,11 +185,11 @@ def main():
 
     # ---- scene (replicated per GPU: every rank runs the same deterministic device build) ----
     sc = scenes.fractal_terrain(n=a.terrain_n)
+    with pt.PathTracer(sc.width, sc.height, device=local, seed=1, background=sc.background) as cold:   # first build in the process: module load, fresh
+        build_first_ms = float(cold.load(sc).build_ms)                                                # device memory mapped into the scratch pool
     tr = pt.PathTracer(sc.width, sc.height, device=local, seed=1, background=sc.background)
-    bs = tr.load(sc)
-    with pt.PathTracer(sc.width, sc.height, device=local, seed=1, background=sc.background) as tr2:   # second build: steady state (kernels loaded, pool warm)
-        bs2 = tr2.load(sc)
-        build_steady_ms, sort_steady_ms = float(bs2.build_ms), float(bs2.sort_ms)
+    bs = tr.load(sc)                                                                                  # steady state: what a rebuild costs
+    build_steady_ms, sort_steady_ms = float(bs.build_ms), float(bs.sort_ms)
     lo, hi = np.asarray(bs.scene_lo[:], np.float64), np.asarray(bs.scene_hi[:], np.float64)
     nrays = 1 << a.log2_rays
     rays = scenes.incoherent_rays(lo, hi, nrays, seed=4 + rank)      # weak scaling: one full set per rank
@@ -296,7 +296,7 @@ def main():
             "hit_id_mismatches": mismatches, "hit_t_max_ulp": max_ulp, "brute_force_mismatches": brute_mismatches,
             "spp_per_s": spp_per_s, "render_ms": render_ms, "render_mrays_per_s": (render_rays / (render_ms * 1e-3) / 1e6) if render_ms else None,
             "frame_mean_radiance": frame_mean,
-            "build": {"build_ms_first": bs.build_ms, "build_ms": build_steady_ms, "sort_ms": sort_steady_ms, "nodes8": int(bs.num_nodes8),
+            "build": {"build_ms_first": build_first_ms, "build_ms": build_steady_ms, "sort_ms": sort_steady_ms, "nodes8": int(bs.num_nodes8),
                       "device_bytes": int(bs.device_bytes), "mtris_per_s": bs.num_triangles / (build_steady_ms * 1e-3) / 1e6,
                       "hbm_frac_at_450B_per_tri": bs.num_triangles * 450.0 / (build_steady_ms * 1e-3) / 1e9 / peak}}
     print(json.dumps(line), flush=True)
