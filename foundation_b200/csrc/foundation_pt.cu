@@ -491,7 +491,6 @@ int32_t foundation_pt_create(const foundation_pt_config* config, const foundatio
         cudaGetLastError();
     }
     if (const char* e = getenv("FOUNDATION_PT_FETCH_THRESH")) { int v = atoi(e); if (v >= 0 && v <= 32) ctx->fetch_thresh = v; }
-    if (const char* e = getenv("FOUNDATION_PT_OPTS")) { ctx->fetch_thresh |= (atoi(e) & 0xff) << 8; }   // 1 prefetch, 2 triangles evict-first, 4 nodes evict-last
     if (const char* e = getenv("FOUNDATION_PT_TRACE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->trace_blocks_per_sm = v; }
     ctx->mats.push_back(PtMaterial{0.8f, 0.8f, 0.8f, 0.5f, 0, 0, 0, 0});
     *out_ctx = ctx;

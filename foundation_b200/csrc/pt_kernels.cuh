@@ -181,9 +181,7 @@ __global__ void __launch_bounds__(PT_SCAN_THREADS) k_scan_add(uint32_t* out, uin
 
 // ---------------------------------------------------------------------------------------------------
 // A2: stable LSD radix sort of (uint64 key, uint32 value), 8 bits per pass.
-// Per pass: per-tile digit histogram -> exclusive scan over [digit][tile] -> stable scatter.  Stability
-// inside a tile: rounds in order, warps in order (shared prefix over per-warp digit counts), lanes in order
-// (match_any + popc of lower lanes).
+// Per pass: per-tile digit histogram -> exclusive scan over [digit][tile] -> stable scatter with a tile-local sort.
 // ---------------------------------------------------------------------------------------------------
 #define PT_RS_THREADS 256
 #define PT_RS_ROUNDS 16
@@ -203,32 +201,85 @@ __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_hist(const uint64_t* keys,
     tile_hist[threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(PT_RS_THREADS) k_rs_scatter(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout, uint32_t n,
-                                                              int shift, const uint32_t* tile_off, uint32_t num_tiles) {
-    __shared__ uint32_t wcnt[PT_RS_THREADS / 32][256];
+// Scatter of one pass.  Each CTA sorts its 4096-key tile locally first, so global writes are runs of consecutive keys per digit
+// (the first version wrote every 8-byte key to its own 32-byte sector and reached 15 % of HBM peak):
+//   1. warp w loads keys [512 w, 512 w + 512) of the tile, 16 per lane, every load coalesced (order in the tile = w, i, lane);
+//   2. rank inside the warp: match_any groups equal digits, a per-warp shared counter carries the running count;
+//   3. one pass over the 8 warp counters per digit + a block scan over the 256 digits give every key its tile-local position;
+//   4. keys go to shared memory at that position, are read back in order and written to global_offset[digit] + run index;
+//   5. values take the same route through the same shared buffer.
+#define PT_RS_KEYS (PT_RS_TILE / PT_RS_THREADS)
+__global__ void __launch_bounds__(PT_RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
+                                                              uint32_t* __restrict__ vout, uint32_t n, int shift, const uint32_t* __restrict__ tile_off,
+                                                              uint32_t num_tiles) {
+    __shared__ uint32_t wh[PT_RS_THREADS / 32][256];
+    __shared__ uint32_t dstart[256], goff[256];
+    __shared__ uint64_t sbuf[PT_RS_TILE];
+    uint32_t* svals = reinterpret_cast<uint32_t*>(sbuf);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint32_t run = tile_off[tid * num_tiles + blockIdx.x];   // next output position of digit `tid` for this tile
     const uint32_t base = blockIdx.x * PT_RS_TILE;
-    for (int r = 0; r < PT_RS_ROUNDS; ++r) {
-        uint32_t i = base + r * PT_RS_THREADS + tid;
-        bool valid = i < n;
-        uint64_t key = valid ? kin[i] : 0ull;
-        uint32_t val = valid ? vin[i] : 0u;
-        uint32_t dig = valid ? ((uint32_t)(key >> shift) & 255u) : (0x10000u + lane);
+    const uint32_t n_valid = min((uint32_t)PT_RS_TILE, n - base);
+    const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-        for (int w = 0; w < PT_RS_THREADS / 32; ++w) wcnt[w][tid] = 0;
-        __syncthreads();
-        uint32_t peers = __match_any_sync(PT_FULL, dig);
-        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank == 0) wcnt[warp][dig] = __popc(peers);
-        __syncthreads();
-        uint32_t acc = run;
+    for (int w = 0; w < PT_RS_THREADS / 32; ++w) wh[w][tid] = 0;
+    uint64_t key[PT_RS_KEYS];
+    uint32_t lp[PT_RS_KEYS];
 #pragma unroll
-        for (int w = 0; w < PT_RS_THREADS / 32; ++w) { uint32_t c = wcnt[w][tid]; wcnt[w][tid] = acc; acc += c; }
-        run = acc;
-        __syncthreads();
-        if (valid) { uint32_t pos = wcnt[warp][dig] + rank; kout[pos] = key; vout[pos] = val; }
-        __syncthreads();
+    for (int i = 0; i < PT_RS_KEYS; ++i) {
+        uint32_t j = warp * (32 * PT_RS_KEYS) + i * 32 + lane;
+        key[i] = j < n_valid ? kin[base + j] : ~0ull;     // padding sorts to the very end of the tile and is never written
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PT_RS_KEYS; ++i) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+        uint32_t peers = __match_any_sync(PT_FULL, d);
+        uint32_t old = wh[warp][d];
+        __syncwarp();
+        if (lane == (uint32_t)__ffs(peers) - 1u) wh[warp][d] = old + (uint32_t)__popc(peers);
+        __syncwarp();
+        lp[i] = old + (uint32_t)__popc(peers & lt);       // rank of this key among the warp's keys with the same digit
+    }
+    __syncthreads();
+    {   // thread `tid` owns digit `tid`: exclusive prefix over the warps, then over the digits
+        uint32_t acc = 0;
+#pragma unroll
+        for (int w = 0; w < PT_RS_THREADS / 32; ++w) { uint32_t c = wh[w][tid]; wh[w][tid] = acc; acc += c; }
+        uint32_t total;
+        dstart[tid] = pt_block_excl_scan(acc, &total);
+        goff[tid] = tile_off[tid * num_tiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PT_RS_KEYS; ++i) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+        lp[i] += dstart[d] + wh[warp][d];
+        sbuf[lp[i]] = key[i];
+    }
+    __syncthreads();
+    uint32_t outpos[PT_RS_KEYS];
+#pragma unroll
+    for (int k = 0; k < PT_RS_KEYS; ++k) {
+        uint32_t j = k * PT_RS_THREADS + tid;
+        outpos[k] = 0xffffffffu;
+        if (j < n_valid) {
+            uint64_t kk = sbuf[j];
+            uint32_t d = (uint32_t)(kk >> shift) & 255u;
+            outpos[k] = goff[d] + (j - dstart[d]);
+            kout[outpos[k]] = kk;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PT_RS_KEYS; ++i) {
+        uint32_t j = warp * (32 * PT_RS_KEYS) + i * 32 + lane;
+        if (j < n_valid) svals[lp[i]] = vin[base + j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PT_RS_KEYS; ++k) {
+        uint32_t j = k * PT_RS_THREADS + tid;
+        if (j < n_valid) vout[outpos[k]] = svals[j];
     }
 }
 
@@ -372,8 +423,6 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
     bool active = false, drained = false;   // drained: the global queue is empty (warp-uniform once set)
     unsigned long long idx = 0;
     const uint32_t lane = pt_lane();
-    const int opts = fetch_thresh >> 8;   // tuning bits ride in the upper bytes of the threshold argument
-    fetch_thresh &= 0xff;
     for (;;) {
         uint32_t need = __ballot_sync(PT_FULL, !active);
         if (need && !drained) {
@@ -395,7 +444,7 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
         }
         if (!__any_sync(PT_FULL, active)) break;
         while (active) {
-            if (pt_trav_step<ANY, TWO_LEVEL>(sc, &st, stack, &best, cnt, opts) == PT_STEP_DONE) {
+            if (pt_trav_step<ANY, TWO_LEVEL>(sc, &st, stack, &best, cnt) == PT_STEP_DONE) {
                 if (st.overflow) atomicOr(status, 1u);
                 job.store(idx, best);
                 active = false;

@@ -32,24 +32,8 @@ PT_HD PtU4 pt_load4(const PtU4* p) {   // read-only 128-bit load (LDG.E.128.CONS
     uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
     PtU4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
 }
-// Triangle words: 480 MB touched at random, essentially never re-used while in L2 -> tag them evict-first so they do not push the
-// 111 MB node array (which IS re-used by every ray) out of the 126 MB L2.  Node words are tagged evict-last.
-PT_HD PtU4 pt_load4_stream(const PtU4* p) {
-    PtU4 r; unsigned long long pol;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
-    return r;
-}
-PT_HD PtU4 pt_load4_keep(const PtU4* p) {
-    PtU4 r; unsigned long long pol;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
-    return r;
-}
 #else
 PT_HD PtU4 pt_load4(const PtU4* p) { return *p; }
-PT_HD PtU4 pt_load4_stream(const PtU4* p) { return *p; }
-PT_HD PtU4 pt_load4_keep(const PtU4* p) { return *p; }
 #endif
 
 // The whole scene as the traversal sees it.
@@ -182,20 +166,13 @@ PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax
     s->tg.x = 0; s->tg.y = 0;
 }
 
-#if defined(__CUDA_ARCH__)
-PT_HD void pt_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#else
-PT_HD void pt_prefetch(const void*) {}
-#endif
-
 // ANY = true: occlusion query, finishes as soon as any triangle is hit in (tmin, tmax).
 // One step = at most one triangle test (or instance entry) followed, if the lane then has no triangle left, by at most one
 // node visit.  A lane whose node produced a single triangle therefore does both in one iteration, lanes with more pending
 // triangles spend extra iterations in the (short) triangle block only; the triangles of a node are always tested before
 // any of its children is visited, so the visit order — and the node / triangle counters — equal the oracle's.
 template <bool ANY, bool TWO_LEVEL, class Counter>
-PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHitRec* best, Counter& cnt, int opts = 0) {
-    const bool prefetch = opts & 1, tri_stream = opts & 2, node_keep = opts & 4;   // tuning switches (A/B measured)
+PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHitRec* best, Counter& cnt) {
     const bool do_tri = s->tg.y != 0;
     const bool leaf_tri = !TWO_LEVEL || s->in_blas;
     // the node visit of this step happens iff the lane has no triangle left after (at most) one test; whether it does is known
@@ -210,8 +187,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
         if (leaf_tri) {
             tri_index = s->tri_base + s->tg.x + k;
             const PtU4* tp = sc.tris + 3 * (size_t)tri_index;
-            if (tri_stream) { ta = pt_load4_stream(tp); tb = pt_load4_stream(tp + 1); tc = pt_load4_stream(tp + 2); }
-            else { ta = pt_load4(tp); tb = pt_load4(tp + 1); tc = pt_load4(tp + 2); }
+            ta = pt_load4(tp); tb = pt_load4(tp + 1); tc = pt_load4(tp + 2);
         }
     }
     if (do_node) {
@@ -224,8 +200,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
             stack[s->sp++] = s->ng;
         }
         const PtU4* np = sc.nodes + 5 * (size_t)(s->node_base + child);
-        if (node_keep) { n0 = pt_load4_keep(np); n1 = pt_load4_keep(np + 1); n2 = pt_load4_keep(np + 2); n3 = pt_load4_keep(np + 3); n4 = pt_load4_keep(np + 4); }
-        else { n0 = pt_load4(np); n1 = pt_load4(np + 1); n2 = pt_load4(np + 2); n3 = pt_load4(np + 3); n4 = pt_load4(np + 4); }
+        n0 = pt_load4(np); n1 = pt_load4(np + 1); n2 = pt_load4(np + 2); n3 = pt_load4(np + 3); n4 = pt_load4(np + 4);
     }
     if (do_tri) {
         if (leaf_tri) {
@@ -254,20 +229,6 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
         uint32_t hits = pt_node_hits(n0, n1, n2, n3, n4, s->r, s->tmin, best->t);
         s->ng.x = n1.x; s->ng.y = (hits & 0xff000000u) | (n0.w >> 24);
         s->tg.x = n1.y; s->tg.y = hits & 0x00ffffffu;
-        if (prefetch && (!TWO_LEVEL || s->in_blas)) {
-            // every triangle this node just queued will be fetched in a later iteration, one DRAM round trip each: start them all now
-            uint32_t m = s->tg.y;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int i = 0; i < 4; ++i) {
-                if (m) {
-                    const PtU4* tp = sc.tris + 3 * (size_t)(s->tri_base + s->tg.x + (uint32_t)pt_ffs0(m));
-                    pt_prefetch(tp); pt_prefetch(tp + 2);
-                    m &= m - 1u;
-                }
-            }
-        }
     }
     // both groups empty: pop the next group (a node group keeps its hit bits in the top byte, a triangle group has none)
     while (!s->tg.y && !(s->ng.y & 0xff000000u)) {
