@@ -122,6 +122,7 @@ struct foundation_pt_context {
     DevBuf d_nodes_all, d_tris_all, d_instances, d_inst_in, d_mesh_info, d_mats, d_lights;
     std::vector<PtMeshInfo> mesh_info;
     DevBuf d_tlas_order; uint32_t tlas_nodes = 0, num_inst = 0;
+    bool flat_valid = false, tlas_only_commit = false; size_t flat_meshes = 0; uint32_t flat_tlas_cap = 0;
     PtSceneView view{};
     uint32_t num_lights = 0; float light_area = 0, ray_eps = 0;
     size_t l2_window_bytes = 0, l2_carve_bytes = 0;
@@ -553,6 +554,7 @@ int32_t foundation_pt_mesh_create(foundation_pt_context* ctx, const void* positi
     if (idx_bytes) { PT_CK(m.d_idx.alloc(idx_bytes)); PT_CK(cudaMemcpyAsync(m.d_idx.p, m.h_idx.data(), idx_bytes, cudaMemcpyHostToDevice, ctx->stream)); }
     PT_CK(cudaStreamSynchronize(ctx->stream));
     ctx->meshes.push_back(std::move(m));
+    ctx->flat_valid = false;
     if (out_mesh_id) *out_mesh_id = (uint32_t)ctx->meshes.size() - 1;
     ctx->committed = false;
     return FOUNDATION_PT_OK;
@@ -616,6 +618,11 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
             memcpy(ctx->mesh_info[k].lo, ctx->meshes[k].lo, 12); memcpy(ctx->mesh_info[k].hi, ctx->meshes[k].hi, 12);
             ctx->mesh_info[k].pad = ctx->meshes[k].pad; ctx->mesh_info[k].ntris = ctx->meshes[k].ntris; ctx->mesh_info[k].nnodes = ctx->meshes[k].num_nodes;
         }
+        uint32_t blas_nodes = 0, blas_tris = 0;
+        for (size_t k = 0; k < ctx->meshes.size(); ++k) {
+            ctx->mesh_info[k].node_base = blas_nodes; ctx->mesh_info[k].tri_base = blas_tris;
+            blas_nodes += ctx->meshes[k].num_nodes; blas_tris += ctx->meshes[k].ntris;
+        }
         PT_CK(ctx->d_inst_in.alloc((size_t)ni * sizeof(PtInstance))); PT_CK(ctx->d_mesh_info.alloc(ctx->mesh_info.size() * sizeof(PtMeshInfo)));
         PT_CK(cudaMemcpyAsync(ctx->d_inst_in.p, rec.data(), (size_t)ni * sizeof(PtInstance), cudaMemcpyHostToDevice, ctx->stream));
         PT_CK(cudaMemcpyAsync(ctx->d_mesh_info.p, ctx->mesh_info.data(), ctx->mesh_info.size() * sizeof(PtMeshInfo), cudaMemcpyHostToDevice, ctx->stream));
@@ -634,21 +641,26 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
         if (rc) return rc;
         sort_ms += out.sort_ms;
         ctx->tlas_nodes = out.num_nodes;
-        uint32_t nb = out.num_nodes, tb = 0;
-        for (size_t k = 0; k < ctx->meshes.size(); ++k) { ctx->mesh_info[k].node_base = nb; ctx->mesh_info[k].tri_base = tb; nb += ctx->meshes[k].num_nodes; tb += ctx->meshes[k].ntris; }
-        PT_CK(cudaMemcpyAsync(ctx->d_mesh_info.p, ctx->mesh_info.data(), ctx->mesh_info.size() * sizeof(PtMeshInfo), cudaMemcpyHostToDevice, ctx->stream));
         PT_CK(ctx->d_instances.alloc((size_t)ni * sizeof(PtInstance)));
         PT_LAUNCH(ctx, k_write_instances, grid_for(ctx, ni, 256, 8), 256, ctx->d_inst_in.as<PtInstance>(), ni, out.order.as<uint32_t>(), out.leaf_seq.as<uint32_t>(),
                   ctx->d_mesh_info.as<PtMeshInfo>(), ctx->d_instances.as<PtInstance>());
-        // flat arrays [TLAS | BLAS 0 | BLAS 1 ...]
-        PT_CK(ctx->d_nodes_all.alloc((size_t)nb * sizeof(PtNode8))); PT_CK(ctx->d_tris_all.alloc((size_t)tb * sizeof(PtTri)));
-        PT_CK(cudaMemcpyAsync(ctx->d_nodes_all.p, out.nodes.p, (size_t)out.num_nodes * sizeof(PtNode8), cudaMemcpyDeviceToDevice, ctx->stream));
-        for (size_t k = 0; k < ctx->meshes.size(); ++k) {
-            PT_CK(cudaMemcpyAsync(ctx->d_nodes_all.as<PtNode8>() + ctx->mesh_info[k].node_base, ctx->meshes[k].d_nodes.p, (size_t)ctx->meshes[k].num_nodes * sizeof(PtNode8),
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
-            PT_CK(cudaMemcpyAsync(ctx->d_tris_all.as<PtTri>() + ctx->mesh_info[k].tri_base, ctx->meshes[k].d_tris.p, (size_t)ctx->meshes[k].ntris * sizeof(PtTri),
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        // flat arrays [BLAS 0 | BLAS 1 | ... | TLAS]: the BLAS part only depends on the meshes, so a commit that follows a mere
+        // instances_set (moving objects) rebuilds and rewrites the TLAS tail only
+        const uint32_t tlas_cap = ni > 64 ? ni : 64;     // a TLAS over ni single-instance leaves never has more than ni nodes
+        const bool reuse = ctx->flat_valid && ctx->flat_meshes == ctx->meshes.size() && ctx->flat_tlas_cap >= out.num_nodes;
+        if (!reuse) {
+            PT_CK(ctx->d_nodes_all.alloc(((size_t)blas_nodes + tlas_cap) * sizeof(PtNode8))); PT_CK(ctx->d_tris_all.alloc((size_t)blas_tris * sizeof(PtTri)));
+            for (size_t k = 0; k < ctx->meshes.size(); ++k) {
+                PT_CK(cudaMemcpyAsync(ctx->d_nodes_all.as<PtNode8>() + ctx->mesh_info[k].node_base, ctx->meshes[k].d_nodes.p, (size_t)ctx->meshes[k].num_nodes * sizeof(PtNode8),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+                PT_CK(cudaMemcpyAsync(ctx->d_tris_all.as<PtTri>() + ctx->mesh_info[k].tri_base, ctx->meshes[k].d_tris.p, (size_t)ctx->meshes[k].ntris * sizeof(PtTri),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            ctx->flat_valid = true; ctx->flat_meshes = ctx->meshes.size(); ctx->flat_tlas_cap = tlas_cap;
         }
+        ctx->tlas_only_commit = reuse;
+        PT_CK(cudaMemcpyAsync(ctx->d_nodes_all.as<PtNode8>() + blas_nodes, out.nodes.p, (size_t)out.num_nodes * sizeof(PtNode8), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->view.tlas_base = blas_nodes;
         PtBuildParams hbp;
         PT_CK(cudaMemcpyAsync(&hbp, bp.p, sizeof hbp, cudaMemcpyDeviceToHost, ctx->stream));
         PT_CK(cudaStreamSynchronize(ctx->stream));
@@ -662,7 +674,7 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
         memcpy(ctx->wlo, m.lo, 12); memcpy(ctx->whi, m.hi, 12);
         memcpy(ctx->mesh_info[0].lo, m.lo, 12); memcpy(ctx->mesh_info[0].hi, m.hi, 12);
         ctx->mesh_info[0].pad = m.pad; ctx->mesh_info[0].ntris = m.ntris; ctx->mesh_info[0].nnodes = m.num_nodes;
-        ctx->d_nodes_all.release(); ctx->d_tris_all.release(); ctx->d_instances.release();
+        ctx->d_nodes_all.release(); ctx->d_tris_all.release(); ctx->d_instances.release(); ctx->flat_valid = false; ctx->view.tlas_base = 0;
         ctx->view.nodes = m.d_nodes.as<PtU4>(); ctx->view.tris = m.d_tris.as<PtU4>(); ctx->view.instances = nullptr;
     }
     // lights — instance order, then input triangle order.  The emissive triangles of each mesh are found on the device
@@ -780,6 +792,17 @@ int32_t foundation_pt_read_accum(foundation_pt_context* ctx, float* rgba, size_t
     cudaSetDevice(ctx->device);
     if (!ctx->d_accum.p) { memset(rgba, 0, need); return FOUNDATION_PT_OK; }
     PT_CK(cudaMemcpyAsync(rgba, ctx->d_accum.p, need, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_write_accum(foundation_pt_context* ctx, const float* rgba, size_t size_bytes) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    size_t need = (size_t)ctx->cfg.width * ctx->cfg.height * 16;
+    if (!rgba || size_bytes < need) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "write_accum: buffer too small");
+    cudaSetDevice(ctx->device);
+    if (!ctx->d_accum.p) PT_CK(ctx->d_accum.alloc(need));
+    PT_CK(cudaMemcpyAsync(ctx->d_accum.p, rgba, need, cudaMemcpyHostToDevice, ctx->stream));
     PT_CK(cudaStreamSynchronize(ctx->stream));
     return FOUNDATION_PT_OK;
 }
@@ -947,7 +970,7 @@ int32_t foundation_pt_tlas_download(foundation_pt_context* ctx, void* nodes, siz
     if (out_num_nodes) *out_num_nodes = ctx->tlas_nodes;
     if (out_num_instances) *out_num_instances = ctx->two_level ? ctx->num_inst : 0;
     if (!ctx->two_level) return FOUNDATION_PT_OK;
-    if (nodes) { if (nodes_bytes < (size_t)ctx->tlas_nodes * 80) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "tlas_download: nodes buffer too small"); PT_CK(cudaMemcpy(nodes, ctx->d_nodes_all.p, (size_t)ctx->tlas_nodes * 80, cudaMemcpyDeviceToHost)); }
+    if (nodes) { if (nodes_bytes < (size_t)ctx->tlas_nodes * 80) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "tlas_download: nodes buffer too small"); PT_CK(cudaMemcpy(nodes, ctx->d_nodes_all.as<PtNode8>() + ctx->view.tlas_base, (size_t)ctx->tlas_nodes * 80, cudaMemcpyDeviceToHost)); }
     if (order) { if (order_bytes < (size_t)ctx->num_inst * 4) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "tlas_download: order buffer too small"); PT_CK(cudaMemcpy(order, ctx->d_tlas_order.p, (size_t)ctx->num_inst * 4, cudaMemcpyDeviceToHost)); }
     return FOUNDATION_PT_OK;
 }

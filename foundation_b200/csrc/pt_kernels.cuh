@@ -436,7 +436,7 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
                 if (idx < n) {
                     pt_v3 o, d; float tmin, tmax;
                     job.load(idx, &o, &d, &tmin, &tmax);
-                    pt_trav_init<TWO_LEVEL>(&st, o, d, tmin, tmax, &best);
+                    pt_trav_init<TWO_LEVEL>(&st, o, d, tmin, tmax, &best, sc.tlas_base);
                     active = true;
                 } else got_none = true;
             }

@@ -38,9 +38,10 @@ PT_HD PtU4 pt_load4(const PtU4* p) { return *p; }
 
 // The whole scene as the traversal sees it.
 struct PtSceneView {
-    const PtU4* nodes;        // all BVH8 nodes: [TLAS | BLAS 0 | BLAS 1 ...] when two_level, else one BLAS
+    const PtU4* nodes;        // all BVH8 nodes: [BLAS 0 | BLAS 1 ... | TLAS] when two_level (any order works: bases are explicit), else one BLAS
     const PtU4* tris;         // all triangles, 3 x 16 B each, BLAS after BLAS, leaf order
     const PtU4* instances;    // PtInstance records in TLAS leaf order, 7 x 16 B each (two_level only)
+    uint32_t tlas_base;       // index of the TLAS root in `nodes` (the TLAS sits after the BLAS so it can be rebuilt alone)
 };
 
 struct PtRayCtx {
@@ -152,7 +153,7 @@ struct PtTravState {
 enum { PT_STEP_RUNNING = 0, PT_STEP_DONE = 1 };
 
 template <bool TWO_LEVEL>
-PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best) {
+PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best, uint32_t tlas_base = 0) {
     best->t = tmax; best->U = 0.0f; best->V = 0.0f; best->ad = 1.0f; best->prim = PT_NONE; best->inst = PT_NONE;
     best->tidx = 0; best->iidx = 0;
     pt_ray_ctx(&s->world, o, d);
@@ -160,7 +161,7 @@ PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax
     s->tmin = tmin;
     s->sp = 0; s->overflow = false;
     s->in_blas = !TWO_LEVEL;
-    s->node_base = 0; s->tri_base = 0; s->cur_inst = TWO_LEVEL ? PT_NONE : 0u; s->cur_iidx = 0;
+    s->node_base = TWO_LEVEL ? tlas_base : 0u; s->tri_base = 0; s->cur_inst = TWO_LEVEL ? PT_NONE : 0u; s->cur_iidx = 0;
     // root: one pending child of a virtual parent with child_base 0 and an empty imask, so popc(...) = 0 -> node 0
     s->ng.x = 0; s->ng.y = 0x80000000u;
     s->tg.x = 0; s->tg.y = 0;
@@ -235,7 +236,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
         if (s->sp == 0) return PT_STEP_DONE;
         PtU2 e = stack[--s->sp];
         if (TWO_LEVEL && e.x == PT_NONE && e.y == 0) {   // leaving an instance
-            s->r = s->world; s->in_blas = false; s->node_base = 0; s->tri_base = 0; s->cur_inst = PT_NONE;
+            s->r = s->world; s->in_blas = false; s->node_base = sc.tlas_base; s->tri_base = 0; s->cur_inst = PT_NONE;
             continue;
         }
         if (e.y & 0xff000000u) s->ng = e; else { s->tg = e; s->ng.x = 0; s->ng.y = 0; }
@@ -248,7 +249,7 @@ template <bool ANY, bool TWO_LEVEL, class Counter>
 PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best, Counter& cnt) {
     PtTravState s;
     PtU2 stack[PT_STACK_SIZE];
-    pt_trav_init<TWO_LEVEL>(&s, o, d, tmin, tmax, best);
+    pt_trav_init<TWO_LEVEL>(&s, o, d, tmin, tmax, best, sc.tlas_base);
     while (pt_trav_step<ANY, TWO_LEVEL>(sc, &s, stack, best, cnt) == PT_STEP_RUNNING) {}
     return !s.overflow;
 }

@@ -54,6 +54,7 @@ SYMBOLS = {
     "foundation_pt_partition_set": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "foundation_pt_render": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "foundation_pt_read_accum": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "foundation_pt_write_accum": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "foundation_pt_resolve_rgba8": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "foundation_pt_accum_device_ptr": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "foundation_pt_trace_closest": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
@@ -203,6 +204,29 @@ class PathTracer:
             out = np.empty((self.height, self.width, 4), np.float32)
         self._check(self._lib.foundation_pt_read_accum(self._ctx, _p(out), out.nbytes))
         return out
+
+    def write_accum(self, accum: np.ndarray):
+        a = np.ascontiguousarray(accum, np.float32)
+        self._check(self._lib.foundation_pt_write_accum(self._ctx, _p(a), a.nbytes))
+
+    # -- checkpoint / resume of a progressive render: the float4 sum + the sample counter + the stream seed
+    def save_checkpoint(self, path: str, samples_done: int, seed: int):
+        acc = self.read_accum()
+        with open(path, "wb") as f:
+            f.write(np.asarray([0x4b435046, 1, self.width, self.height, samples_done, 0], np.uint32).tobytes())   # 'FPCK'
+            f.write(np.asarray([seed], np.uint64).tobytes())
+            f.write(acc.tobytes())
+
+    def load_checkpoint(self, path: str):
+        """Returns (samples_done, seed); continue with render(samples_done, more, bounces) on a context created with that seed."""
+        with open(path, "rb") as f:
+            hdr = np.frombuffer(f.read(24), np.uint32)
+            if hdr[0] != 0x4b435046 or hdr[1] != 1 or hdr[2] != self.width or hdr[3] != self.height:
+                raise ValueError("not a checkpoint of this frame size")
+            seed = int(np.frombuffer(f.read(8), np.uint64)[0])
+            acc = np.frombuffer(f.read(self.width * self.height * 16), np.float32).reshape(self.height, self.width, 4)
+        self.write_accum(acc)
+        return int(hdr[4]), seed
 
     def resolve_rgba8(self) -> np.ndarray:
         out = np.empty((self.height, self.width, 4), np.uint8)

@@ -168,6 +168,9 @@ FOUNDATION_PT_API int32_t foundation_pt_partition_set(foundation_pt_context* ctx
 FOUNDATION_PT_API int32_t foundation_pt_render(foundation_pt_context* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces);
 /* Linear radiance SUM (not yet divided by spp) as float4 per pixel, row-major from the top-left; w = sample count. */
 FOUNDATION_PT_API int32_t foundation_pt_read_accum(foundation_pt_context* ctx, float* rgba, size_t size_bytes);
+/* Restores an accumulation buffer saved with read_accum (checkpoint / resume of a progressive render; the
+ * reference serialises nothing, §5).  Follow with render(sample_begin = samples already in the buffer, ...). */
+FOUNDATION_PT_API int32_t foundation_pt_write_accum(foundation_pt_context* ctx, const float* rgba, size_t size_bytes);
 /* accum / spp, clamped to [0,1], packed R8G8B8A8_UNORM (the reference's swapchain format, Renderer.cpp:40). */
 FOUNDATION_PT_API int32_t foundation_pt_resolve_rgba8(foundation_pt_context* ctx, uint8_t* rgba8, size_t size_bytes);
 /* Device address of the accumulation buffer (width*height float4) for zero-copy hand-off to a collective

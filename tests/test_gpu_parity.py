@@ -217,3 +217,52 @@ def test_leaf_sizes_and_far_origins(gpu, leaf):
     oh, oi = orc.trace_closest(rays[:20000])
     assert gh[:20000].tobytes() == oh.tobytes() and np.array_equal(gi[:20000], oi)
     tr.close()
+
+
+def test_checkpoint_resume_is_bit_identical(gpu, tmp_path):
+    """Progressive render interrupted and resumed in a NEW context from a file equals the uninterrupted render (§8f rank 4)."""
+    sc = SMALL_SCENES["spheres"]()
+    a = pt.PathTracer(sc.width, sc.height, seed=21, background=sc.background); a.load(sc)
+    a.render(0, 5, 4)
+    ck = str(tmp_path / "frame.fpck")
+    a.save_checkpoint(ck, 5, 21)
+    a.render(5, 3, 4)
+    full = a.read_accum(); a.close()
+    b = pt.PathTracer(sc.width, sc.height, seed=21, background=sc.background); b.load(sc)
+    done, seed = b.load_checkpoint(ck)
+    assert (done, seed) == (5, 21)
+    b.render(done, 3, 4)
+    assert np.array_equal(b.read_accum(), full)
+    b.close()
+
+
+def test_moving_instances_rebuild_only_the_tlas(gpu):
+    """SURVEY.md §8f rank 3 (the reference animates its model matrix every Draw, Renderer.cpp:373): instances_set + scene_commit on an
+    already committed scene keeps every BLAS and the flat BLAS arrays, rebuilds the TLAS, and traces exactly like a fresh build."""
+    sc = SMALL_SCENES["instanced"]()
+    tr = pt.PathTracer(sc.width, sc.height, seed=2, background=sc.background)
+    tr.load(sc)
+    full_launches = tr.stats().kernel_launches
+    blas_before = [x.tobytes() for x in tr.blas_download(0)]
+    moved = sc.instances.copy()
+    rng = np.random.default_rng(3)
+    n = len(moved) - 1                                        # last instance is the light: leave it
+    ang = rng.uniform(0, 2 * np.pi, n); s = rng.uniform(0.7, 1.4, n)
+    T = moved["transform"][:n].copy()
+    T[:, 0] = s * np.cos(ang); T[:, 1] = -s * np.sin(ang); T[:, 4] = s * np.sin(ang); T[:, 5] = s * np.cos(ang); T[:, 10] = s
+    T[:, 3] += rng.uniform(-0.3, 0.3, n); T[:, 7] += rng.uniform(-0.3, 0.3, n); T[:, 11] += rng.uniform(0.0, 0.5, n)
+    moved["transform"][:n] = T
+    tr.instances_set(moved)
+    tr.scene_commit()
+    assert tr.stats().kernel_launches < full_launches, "second commit should skip the BLAS builds"
+    assert [x.tobytes() for x in tr.blas_download(0)] == blas_before
+    sc2 = scenes.Scene(sc.name, sc.meshes, sc.materials, moved, sc.view, sc.proj, sc.width, sc.height, sc.background)
+    orc = OracleScene(sc2)
+    gn, go = tr.tlas_download(); on, oo, _ = orc.tlas()
+    assert np.array_equal(go, oo) and gn.tobytes() == on.tobytes()
+    rays = ray_mix(sc2)
+    gh, gi = tr.trace_closest(rays); oh, oi = orc.trace_closest(rays)
+    assert gh.tobytes() == oh.tobytes() and np.array_equal(gi, oi)
+    tr.render(0, 2, 3)
+    assert np.array_equal(tr.read_accum(), orc.render(sc.width, sc.height, 2, 0, 2, 3, background=sc.background))
+    tr.close()
