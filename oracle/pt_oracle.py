@@ -107,6 +107,12 @@ class OracleScene:
             ids = np.ascontiguousarray(scene.instances["mesh_id"], np.uint32); xf = np.ascontiguousarray(scene.instances["transform"], np.float32)
             self._L.orc_instances_set(self._h, _p(ids), _p(xf), ids.shape[0])
             self.flat = False
+        elif len(scene.meshes) > 1:
+            # same rule as foundation_pt_scene_commit: several meshes and no instance list = every mesh once with the identity transform
+            ids = np.arange(len(scene.meshes), dtype=np.uint32)
+            xf = np.ascontiguousarray(np.tile(np.asarray([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32), (len(scene.meshes), 1)))
+            self._L.orc_instances_set(self._h, _p(ids), _p(xf), ids.shape[0])
+            self.flat = False
         self._L.orc_commit(self._h)
         if scene.view is not None:
             self.camera_set(scene.view, scene.proj)

@@ -6,7 +6,7 @@ import pytest
 
 from foundation_b200 import pt, scenes
 from oracle.pt_oracle import OracleScene
-from tests.util import SMALL_SCENES, assert_hits_equal, ray_mix, rmse
+from tests.util import SMALL_SCENES, assert_hits_equal, multi_mesh_scene, ray_mix, rmse
 
 pytestmark = pytest.mark.gpu
 
@@ -265,4 +265,17 @@ def test_moving_instances_rebuild_only_the_tlas(gpu):
     assert gh.tobytes() == oh.tobytes() and np.array_equal(gi, oi)
     tr.render(0, 2, 3)
     assert np.array_equal(tr.read_accum(), orc.render(sc.width, sc.height, 2, 0, 2, 3, background=sc.background))
+    tr.close()
+
+
+def test_several_meshes_without_instances(gpu):
+    """scene_commit's implicit identity instances (one per mesh) against the oracle's same rule: hits, instance ids, image."""
+    sc = multi_mesh_scene()
+    tr = pt.PathTracer(sc.width, sc.height, seed=4); tr.load(sc)
+    orc = OracleScene(sc)
+    rays = ray_mix(sc, 4096)
+    gh, gi = tr.trace_closest(rays); oh, oi = orc.trace_closest(rays)
+    assert gh.tobytes() == oh.tobytes() and np.array_equal(gi, oi) and set(np.unique(gi[gh["prim"] != 0xFFFFFFFF])) == {0, 1, 2}
+    tr.render(0, 2, 4)
+    assert np.array_equal(tr.read_accum(), orc.render(sc.width, sc.height, 4, 0, 2, 4))
     tr.close()

@@ -12,7 +12,7 @@ import pytest
 from foundation_b200 import scenes
 from oracle import pt_oracle as orc
 from oracle.pt_oracle import HIT_DTYPE, NODE_DTYPE, OracleScene
-from tests.util import SMALL_SCENES, assert_hits_equal, ray_mix
+from tests.util import SMALL_SCENES, assert_hits_equal, multi_mesh_scene, ray_mix
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -278,3 +278,16 @@ def test_far_ray_origins_stay_conservative():
         o = OracleScene(sc, max_leaf=leaf)
         h, i = o.trace_closest(rays); hb, ib = o.trace_closest(rays, brute=True)
         assert_hits_equal(h, i, hb, ib, f"far origins, leaf {leaf}")
+
+
+def test_several_meshes_without_instances_are_instanced_once_each():
+    """Implicit identity instances: the split Cornell box traces and renders like the single-mesh one (prim ids are per mesh)."""
+    sc3 = multi_mesh_scene(); sc1 = scenes.cornell_box(96, 96)
+    o3 = OracleScene(sc3); o1 = OracleScene(sc1)
+    rays = ray_mix(sc1, 2048)
+    h3, i3 = o3.trace_closest(rays); h1, _ = o1.trace_closest(rays); hb, ib = o3.trace_closest(rays, brute=True)
+    assert_hits_equal(h3, i3, hb, ib, "3 meshes: BVH vs exhaustive")
+    base = np.asarray([0, 10, 20])
+    hit = h3["prim"] != 0xFFFFFFFF
+    assert np.array_equal(hit, h1["prim"] != 0xFFFFFFFF) and np.array_equal(h3["t"], h1["t"])
+    assert np.array_equal(base[i3[hit]] + h3["prim"][hit], h1["prim"][hit])

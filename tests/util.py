@@ -11,10 +11,24 @@ SMALL_SCENES = {
 }
 
 
+def multi_mesh_scene():
+    """Three meshes, no instance list (implicit identity instances): the Cornell room, and its two boxes as separate meshes."""
+    sc = scenes.cornell_box(96, 96)
+    m = sc.meshes[0]
+    parts = [(0, 10), (10, 20), (20, 30), (30, 32)]      # room, tall box, short box, light
+    meshes = []
+    for a, b in [(0, 10), (10, 20), (20, 32)]:
+        idx = m.indices[a:b]
+        used, inv = np.unique(idx.reshape(-1), return_inverse=True)
+        meshes.append(scenes.Mesh(np.ascontiguousarray(m.positions[used]), np.ascontiguousarray(inv.reshape(-1, 3).astype(np.uint32)),
+                                  np.ascontiguousarray(m.material_ids[a:b])))
+    return scenes.Scene("cornell_3_meshes", meshes, sc.materials, None, sc.view, sc.proj, sc.width, sc.height)
+
+
 def ray_mix(scene, n_each=4096, seed=4):
     lo, hi = scenes.scene_bounds(scene)
     parts = [scenes.incoherent_rays(lo, hi, n_each, seed), scenes.camera_rays(scene, n_each, seed + 1)]
-    if scene.instances is None:
+    if scene.instances is None and len(scene.meshes) == 1:
         parts.append(scenes.stress_rays(scene, n_each, seed + 2))
     # bounded segments exercise tmin / tmax
     seg = scenes.incoherent_rays(lo, hi, n_each, seed + 3)
