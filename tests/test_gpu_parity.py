@@ -279,3 +279,19 @@ def test_several_meshes_without_instances(gpu):
     tr.render(0, 2, 4)
     assert np.array_equal(tr.read_accum(), orc.render(sc.width, sc.height, 4, 0, 2, 4))
     tr.close()
+
+
+def test_degenerate_and_duplicate_triangles_on_device(gpu):
+    from tests.test_oracle import degenerate_scene
+    sc = degenerate_scene()
+    tr = pt.PathTracer(32, 32); tr.load(sc)
+    orc = OracleScene(sc)
+    gn, gt, go = tr.blas_download(0); on, ot, oo = orc.blas(0)
+    assert np.array_equal(go, oo) and gn.tobytes() == on.tobytes() and gt.tobytes() == ot.tobytes()
+    lo, hi = scenes.scene_bounds(sc)
+    rays = np.concatenate([scenes.incoherent_rays(lo, hi, 20000, 3), scenes.incoherent_rays(np.zeros(3), np.ones(3), 20000, 4)])
+    gh, gi = tr.trace_closest(rays); oh, oi = orc.trace_closest(rays)
+    assert gh.tobytes() == oh.tobytes()
+    tr.rays_upload(rays); tr.rays_trace_brute(); bh, bi = tr.rays_download_hits()
+    assert_hits_equal(gh, gi, bh, bi, "degenerate mesh: device BVH vs device exhaustive")
+    tr.close()

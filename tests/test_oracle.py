@@ -291,3 +291,34 @@ def test_several_meshes_without_instances_are_instanced_once_each():
     hit = h3["prim"] != 0xFFFFFFFF
     assert np.array_equal(hit, h1["prim"] != 0xFFFFFFFF) and np.array_equal(h3["t"], h1["t"])
     assert np.array_equal(base[i3[hit]] + h3["prim"][hit], h1["prim"][hit])
+
+
+def degenerate_scene():
+    """Zero-area triangles (repeated vertex, collinear vertices), duplicated triangles and a far outlier: ragged input the build must
+    survive without NaNs in the tree; degenerate triangles can never be hit (|det| = 0 is rejected)."""
+    rng = np.random.default_rng(2)
+    pos = rng.random((60, 3)).astype(np.float32)
+    idx = rng.integers(0, 60, (200, 3)).astype(np.uint32)
+    idx[::7, 1] = idx[::7, 0]                              # repeated vertex
+    pos[50] = pos[51] * 0.5 + pos[52] * 0.5; idx[5] = (51, 50, 52)    # collinear
+    idx[100:110] = idx[90:100]                             # duplicates
+    pos[59] = (40.0, -30.0, 25.0)                          # outlier stretches the Morton grid
+    return scenes.Scene("degenerate", [scenes.Mesh(pos, idx, np.zeros(200, np.uint32))], np.asarray([[.8, .8, .8, .5, 0, 0, 0, 0]], np.float32))
+
+
+def test_degenerate_and_duplicate_triangles():
+    sc = degenerate_scene()
+    o = OracleScene(sc)
+    nodes, tris, order = o.blas(0)
+    assert np.isfinite(nodes["p"]).all() and sorted(order.tolist()) == list(range(200))
+    lo, hi = scenes.scene_bounds(sc)
+    rays = np.concatenate([scenes.incoherent_rays(lo, hi, 6000, 3), scenes.incoherent_rays(np.zeros(3), np.ones(3), 6000, 4)])
+    h, i = o.trace_closest(rays); hb, ib = o.trace_closest(rays, brute=True)
+    assert_hits_equal(h, i, hb, ib, "degenerate mesh")
+    m = sc.meshes[0]
+    hit = h["prim"][h["prim"] != 0xFFFFFFFF]
+    tri = m.positions[m.indices[hit]].astype(np.float64)
+    area = np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    assert (area > 0).all() and len(hit) > 100
+    dup_hit = hit[(hit >= 100) & (hit < 110)]
+    assert len(dup_hit) == 0, "a duplicated triangle must lose the tie to its lower-index twin"
