@@ -1,9 +1,12 @@
 // Editor.cpp — headless stand-in for the reference's only caller of the renderer (src/Editor/Editor.cpp:13-44):
 // construct the allocator, the device handle and the Renderer, call Draw() in a loop, report allocator bytes at exit.
 // There is no window on the GPU box, so the loop runs a fixed number of frames and writes the result to disk instead of presenting.
-//   usage: foundation_editor <scene.fpts> <frames> <samples_per_draw> <max_bounces> [out.pfm] [out.ppm]
+//   usage: foundation_editor <scene.fpts> <frames> <samples_per_draw> <max_bounces> [out.raw] [out.ppm] [spin_degrees_per_frame]
+// With a spin angle every frame rotates all instances about +Z by frame * angle before drawing, like the reference's per-frame model
+// matrix (src/Renderer/Renderer.cpp:373): TLAS-only rebuild + accumulation restart each Draw().
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,7 +58,20 @@ int main(int argc, char** argv) {
         Renderer::Renderer renderer(device, g_Allocator.Ptr(), scene, /*seed*/ 7);
         renderer.SetQuality(spd, bounces);
         auto t0 = std::chrono::steady_clock::now();
-        for (int i = 0; i < frames; ++i) renderer.Draw();       // Main Loop (Editor.cpp:20-23)
+        const double spin = argc > 7 ? std::atof(argv[7]) : 0.0;
+        std::vector<foundation_pt_instance> moved(scene.instances);
+        for (int i = 0; i < frames; ++i) {                      // Main Loop (Editor.cpp:20-23)
+            if (spin != 0.0 && !moved.empty()) {
+                const double a = (i + 1) * spin * 3.14159265358979323846 / 180.0;
+                const float c = (float)std::cos(a), s = (float)std::sin(a);
+                for (size_t k = 0; k < moved.size(); ++k) {     // model = rotate(angle, +Z) * original (rows of the 3x4)
+                    const float* t = scene.instances[k].transform; float* o = moved[k].transform;
+                    for (int col = 0; col < 4; ++col) { o[col] = c * t[col] - s * t[4 + col]; o[4 + col] = s * t[col] + c * t[4 + col]; o[8 + col] = t[8 + col]; }
+                }
+                renderer.SetInstances(moved.data(), (uint32_t)moved.size());
+            }
+            renderer.Draw();
+        }
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         foundation_pt_build_stats bs = renderer.BuildStats();
         std::printf("frames=%d spp=%u ms=%.3f spp_per_s=%.2f tris=%llu nodes8=%llu build_ms=%.2f\n", frames, renderer.SamplesDone(), ms,

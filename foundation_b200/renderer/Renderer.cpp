@@ -68,6 +68,12 @@ void Renderer::SetQuality(uint32_t samples_per_draw, uint32_t max_bounces) {
     m_samples_per_draw = samples_per_draw ? samples_per_draw : 1; m_max_bounces = max_bounces;
 }
 
+void Renderer::SetInstances(const foundation_pt_instance* instances, uint32_t count) {
+    Check(foundation_pt_instances_set(m_ctx, instances, count), "instances_set");
+    Check(foundation_pt_scene_commit(m_ctx, &m_build), "scene_commit");   // TLAS-only: the meshes did not change
+    m_samples_done = 0;
+}
+
 void Renderer::Draw() {
     Check(foundation_pt_render(m_ctx, m_samples_done, m_samples_per_draw, m_max_bounces), "render");
     m_samples_done += m_samples_per_draw;

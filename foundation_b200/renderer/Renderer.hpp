@@ -76,6 +76,9 @@ public:
     Renderer& operator=(const Renderer&) = delete;
     void SetCamera(const float view[16], const float proj[16]);   // the reference rewrites the UBO every Draw (Renderer.cpp:372-380); resets accumulation
     void SetQuality(uint32_t samples_per_draw, uint32_t max_bounces);
+    // Per-frame model matrices, the analogue of `ubo.model = glm::rotate(..., time * 90deg, +Z)` (Renderer.cpp:373): replaces the instance list,
+    // rebuilds only the TLAS (every BLAS is kept) and restarts the accumulation.
+    void SetInstances(const foundation_pt_instance* instances, uint32_t count);
     void Draw();                                                   // one sample batch + resolve to the present image (blocking, like Renderer.cpp:394)
     const uint8_t* PresentImage() const { return m_present_image; }
     uint32_t Width() const { return m_width; }
