@@ -321,3 +321,26 @@ def test_cpp_renderer_host_spinning_instances(gpu, tmp_path):
     acc = np.fromfile(raw, np.float32).reshape(sc.height, sc.width, 4)
     o = OracleScene(sc2).render(sc.width, sc.height, 7, 0, 2, 3, background=sc.background)
     assert np.array_equal(acc, o)
+
+
+def test_pathological_rays_terminate_and_match_oracle(gpu):
+    """NaN / inf / denormal / zero-length / inverted-interval rays: the traversal terminates and reports what the oracle reports."""
+    sc = SMALL_SCENES["terrain"]()
+    tr = pt.PathTracer(sc.width, sc.height); tr.load(sc)
+    orc = OracleScene(sc)
+    lo, hi = scenes.scene_bounds(sc)
+    rays = scenes.incoherent_rays(lo, hi, 4096, 8)
+    rays["origin"][0::16, 0] = np.nan
+    rays["direction"][1::16] = (np.inf, 0, -1)
+    rays["direction"][2::16] = (0, 0, 0)
+    rays["direction"][3::16] *= np.float32(1e-42)                 # denormal direction
+    rays["tmax"][4::16] = -1.0                                    # empty interval
+    rays["tmin"][5::16] = np.inf
+    rays["direction"][6::16] *= np.float32(1e30)                  # huge direction: hits at tiny t
+    rays["origin"][7::16] = (1e30, 1e30, 1e30)
+    rays["direction"][8::16, 2] = 0.0                             # axis-parallel rays (zero component -> clamped reciprocal)
+    rays["direction"][9::16, :2] = 0.0
+    gh, gi = tr.trace_closest(rays); oh, oi = orc.trace_closest(rays)
+    assert np.array_equal(gh["prim"], oh["prim"]) and gh.tobytes() == oh.tobytes()
+    assert np.array_equal(tr.trace_any(rays), orc.trace_any(rays))
+    tr.close()

@@ -322,3 +322,31 @@ def test_degenerate_and_duplicate_triangles():
     assert (area > 0).all() and len(hit) > 100
     dup_hit = hit[(hit >= 100) & (hit < 110)]
     assert len(dup_hit) == 0, "a duplicated triangle must lose the tie to its lower-index twin"
+
+
+def test_bsdf_matches_independent_float64_formula():
+    """The surface model restated in numpy float64 from its definition (Lambert base under (1-F)(1-F), GGX D, height-correlated
+    Smith G2, Schlick F; VNDF pdf) — independent of pt_shading.h — agrees with the shared float32 arithmetic."""
+    rng = np.random.default_rng(9)
+
+    def ref(mat, wo, wi):
+        base = np.asarray(mat[:3], np.float64); rough, metal = float(mat[3]), float(mat[7])
+        kd = base * (1 - metal); f0 = 0.04 + (base - 0.04) * metal
+        alpha = max(rough * rough, 1e-3); a2 = alpha * alpha
+        h = (wo + wi) / np.linalg.norm(wo + wi)
+        D = a2 / (np.pi * ((h[2] ** 2) * (a2 - 1) + 1) ** 2)
+        lam = lambda c: 0.5 * (np.sqrt(1 + a2 * (1 - c * c) / (c * c)) - 1)
+        G2 = 1 / (1 + lam(wo[2]) + lam(wi[2])); G1 = 1 / (1 + lam(wo[2]))
+        F = f0 + (1 - f0) * (1 - max(wo @ h, 0)) ** 5
+        Fo = f0 + (1 - f0) * (1 - wo[2]) ** 5; Fi = f0 + (1 - f0) * (1 - wi[2]) ** 5
+        f = kd / np.pi * (1 - Fo) * (1 - Fi) + F * D * G2 / (4 * wo[2] * wi[2])
+        p_spec = 0.5 + 0.5 * metal
+        pdf = p_spec * G1 * D / (4 * wo[2]) + (1 - p_spec) * wi[2] / np.pi
+        return f, pdf
+
+    for mat in MATS + [[0.3, 0.6, 0.9, 0.7, 0, 0, 0, 0.5]]:
+        for _ in range(200):
+            v = rng.normal(size=(2, 3)); v[:, 2] = np.abs(v[:, 2]) + 0.05; v /= np.linalg.norm(v, axis=1, keepdims=True)
+            f, pdf = orc.bsdf_eval(mat, v[0].astype(np.float32), v[1].astype(np.float32))
+            fr, pr = ref(mat, v[0].astype(np.float32).astype(np.float64), v[1].astype(np.float32).astype(np.float64))
+            assert np.allclose(f, fr, rtol=2e-3, atol=1e-6) and abs(pdf - pr) <= 2e-3 * max(pr, 1e-3), (mat, f, fr, pdf, pr)
