@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(128) k_trace_brute(PtSceneView sc, const PtIns
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < n;
     float4 a = valid ? rays[2 * i] : make_float4(0, 0, 0, 0), b = valid ? rays[2 * i + 1] : make_float4(0, 0, 0, 0);
-    PtHitRec best; best.t = b.w; best.U = best.V = 0; best.ad = 1; best.prim = PT_NONE; best.inst = PT_NONE; best.tidx = best.iidx = 0;
+    PtHitRec best; best.t = b.w; best.U = best.V = 0; best.ad = 1; best.prim = PT_NONE; best.inst = PT_NONE; best.tidx = best.iidx = 0; best.mat = 0;
     PtNoCount nc;
     uint32_t ninst = TWO_LEVEL ? num_inst : 1u;
     for (uint32_t ii = 0; ii < ninst; ++ii) {
@@ -594,10 +594,7 @@ struct PtExtendJob {
     __device__ __forceinline__ void store(unsigned long long j, const PtHitRec& h) const {
         uint32_t s = w.active[j];
         uint32_t key = PT_KEY_MISS;
-        if (h.prim != PT_NONE) {
-            uint32_t mat = __ldg(reinterpret_cast<const uint32_t*>(tris + 3 * (size_t)h.tidx + 1) + 3);
-            key = min(mat, PT_KEY_BUCKETS - 1u);
-        }
+        if (h.prim != PT_NONE) key = min(h.mat, PT_KEY_BUCKETS - 1u);
         w.hit[s] = make_float4(h.t, __uint_as_float(h.tidx), __uint_as_float(h.iidx), __uint_as_float(key));
     }
 };

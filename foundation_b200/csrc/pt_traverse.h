@@ -42,6 +42,7 @@ struct PtSceneView {
     const PtU4* tris;         // all triangles, 3 x 16 B each, BLAS after BLAS, leaf order
     const PtU4* instances;    // PtInstance records in TLAS leaf order, 7 x 16 B each (two_level only)
     uint32_t tlas_base;       // index of the TLAS root in `nodes` (the TLAS sits after the BLAS so it can be rebuilt alone)
+    uint32_t zero;            // always 0, but only known at run time: see pt_test_tri_words
 };
 
 struct PtRayCtx {
@@ -110,27 +111,35 @@ struct PtHitRec {
     float t, U, V, ad;   // undivided barycentrics U, V and |det|
     uint32_t prim, inst;
     uint32_t tidx, iidx;  // position of the triangle / instance record in the leaf-ordered device arrays (for shading)
+    uint32_t mat;         // material id of the hit triangle (word 1 .w of the record).  Keeping it live also stops ptxas from recycling
+                          // that register as a scratch right behind the load (a write-after-write stall that serialised the triangle
+                          // and node fetches and cost 8 %)
 };
 
 // one ray / triangle test against the current best; a, b, c are the triangle's three 16-byte words
+// `keep` is PtSceneView::zero (0 at run time, opaque to the compiler): OR-ing the two unused .w lanes of the triangle words into
+// prim through it keeps those registers LIVE until the hit update.  Without it ptxas recycles the dead lane of the 128-bit load as
+// a scratch register for the very next ALU instruction, which then waits (write-after-write) for the load to land BEFORE the
+// node loads of the same step are issued — the triangle and node round trips serialise again and the kernel loses 8 %
+// (measured on the same box: 6188 vs 6728 Mrays/s; a SASS scan for such hazards is in scripts/sass_waw.py).
 template <class Counter>
 PT_HD void pt_test_tri_words(const PtU4& a, const PtU4& b, const PtU4& c, uint32_t tri_index, const PtRayCtx& r, float tmin, uint32_t inst, uint32_t iidx,
-                             PtHitRec* best, Counter& cnt) {
+                             PtHitRec* best, Counter& cnt, uint32_t keep = 0) {
     cnt.tri();
     float t, U, V, ad;
     if (pt_ray_tri(r.o, r.d, pt_mk(pt_u2f(a.x), pt_u2f(a.y), pt_u2f(a.z)), pt_mk(pt_u2f(b.x), pt_u2f(b.y), pt_u2f(b.z)),
                    pt_mk(pt_u2f(c.x), pt_u2f(c.y), pt_u2f(c.z)), &t, &U, &V, &ad)) {
         uint64_t id = ((uint64_t)inst << 32) | a.w, bid = ((uint64_t)best->inst << 32) | best->prim;
         if (pt_closer(t, id, tmin, best->t, bid, best->prim != PT_NONE)) {
-            best->t = t; best->U = U; best->V = V; best->ad = ad; best->prim = a.w; best->inst = inst;
-            best->tidx = tri_index; best->iidx = iidx;
+            best->t = t; best->U = U; best->V = V; best->ad = ad; best->prim = a.w | ((b.w | c.w) & keep); best->inst = inst;
+            best->tidx = tri_index; best->iidx = iidx; best->mat = b.w;
         }
     }
 }
 template <class Counter>
 PT_HD void pt_test_tri(const PtU4* tris, uint32_t tri_index, const PtRayCtx& r, float tmin, uint32_t inst, uint32_t iidx, PtHitRec* best, Counter& cnt) {
     const PtU4 a = pt_load4(tris + 3 * (size_t)tri_index), b = pt_load4(tris + 3 * (size_t)tri_index + 1), c = pt_load4(tris + 3 * (size_t)tri_index + 2);
-    pt_test_tri_words(a, b, c, tri_index, r, tmin, inst, iidx, best, cnt);
+    pt_test_tri_words(a, b, c, tri_index, r, tmin, inst, iidx, best, cnt, 0u);
 }
 
 struct PtNoCount { PT_HDM void node() {} PT_HDM void tri() {} PT_HDM void inst() {} };
@@ -155,7 +164,7 @@ enum { PT_STEP_RUNNING = 0, PT_STEP_DONE = 1 };
 template <bool TWO_LEVEL>
 PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best, uint32_t tlas_base = 0) {
     best->t = tmax; best->U = 0.0f; best->V = 0.0f; best->ad = 1.0f; best->prim = PT_NONE; best->inst = PT_NONE;
-    best->tidx = 0; best->iidx = 0;
+    best->tidx = 0; best->iidx = 0; best->mat = 0;
     pt_ray_ctx(&s->world, o, d);
     s->r = s->world;
     s->tmin = tmin;
@@ -205,7 +214,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
     }
     if (do_tri) {
         if (leaf_tri) {
-            pt_test_tri_words(ta, tb, tc, tri_index, s->r, s->tmin, s->cur_inst, s->cur_iidx, best, cnt);
+            pt_test_tri_words(ta, tb, tc, tri_index, s->r, s->tmin, s->cur_inst, s->cur_iidx, best, cnt, sc.zero);
             if (ANY && best->prim != PT_NONE) return PT_STEP_DONE;
         } else {
             // TLAS leaf: enter the instance.  Save the remaining groups, push the return sentinel.

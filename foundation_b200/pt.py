@@ -93,6 +93,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
                 raise
     lib = C.CDLL(p)
     for name, (res, args) in SYMBOLS.items():
+        if os.environ.get("FOUNDATION_PT_LIB") and not hasattr(lib, name):
+            continue                    # A/B experiments against an older build only
         fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly
         fn.restype = res; fn.argtypes = args
     if path is None:

@@ -68,7 +68,7 @@ struct EmuHit { float t, u, v; uint32_t prim; };
 // mode bit 0: any-hit; two_level != 0: instanced scene.  counters[3] accumulates nodes / tris / instances.
 int emu_trace(const void* nodes, const void* tris, const void* instances, int two_level, const void* rays_, uint64_t n, void* hits_, uint32_t* inst_out,
               uint8_t* occ, int any, uint64_t* counters) {
-    PtSceneView sc{(const PtU4*)nodes, (const PtU4*)tris, (const PtU4*)instances, 0u};   // oracle layout: TLAS first
+    PtSceneView sc{(const PtU4*)nodes, (const PtU4*)tris, (const PtU4*)instances, 0u, 0u};   // oracle layout: TLAS first
     const EmuRay* rays = (const EmuRay*)rays_; EmuHit* hits = (EmuHit*)hits_;
     PtCount c{0, 0, 0};
     int ok = 1;
