@@ -128,8 +128,8 @@ typedef struct foundation_pt_stats {
     uint64_t rays_extend;      /* closest-hit rays traced by the last render call */
     uint64_t rays_shadow;      /* any-hit rays traced by the last render call */
     float last_ms;             /* device time of the last render/trace call (CUDA events on the context's stream) */
-    float trace_ms;            /* of which traversal kernels */
-    float shade_ms;            /* of which shading / sorting / compaction kernels */
+    float trace_ms;            /* device time of the last rays_trace_* call (one traversal kernel)                            */
+    float shade_ms;            /* reserved (0): per-stage times of a render are taken with ncu, see profiles/               */
     uint32_t reserved;
     uint64_t total_launches;   /* since create */
 } foundation_pt_stats;
