@@ -409,7 +409,7 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
         const uint32_t S = ctx->num_slots * batch;
         w.num_slots = S;
         const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8), gtrace = grid_for(ctx, S, 128, trace_blocks(ctx));
-        PtFrame f; f.cam = ctx->cam; f.seed = ctx->cfg.seed; f.width = ctx->cfg.width; f.height = ctx->cfg.height; f.sample = smp;
+        PtFrame f; f.cam = ctx->cam; f.seed = ctx->cfg.seed; f.width = ctx->cfg.width; f.height = ctx->cfg.height; f.sample = smp; f.flags = ctx->cfg.flags;
         smp += batch;
         w.active = ctx->w_active.as<uint32_t>(); w.next = ctx->w_next.as<uint32_t>();
         PT_LAUNCH(ctx, k_raygen, g256, 256, w, f);

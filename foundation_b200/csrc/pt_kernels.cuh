@@ -562,7 +562,7 @@ struct PtWave {
 #define PT_KEY_MISS PT_KEY_BUCKETS
 
 struct PtFrame {
-    PtCamera cam; uint64_t seed; uint32_t width, height, sample;
+    PtCamera cam; uint64_t seed; uint32_t width, height, sample, flags;
 };
 
 // B1: ray generation (one lane per slot)
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(256) k_raygen(PtWave w, PtFrame f) {
         uint32_t ps = s % w.num_pixels, k = s / w.num_pixels;     // several samples of every owned pixel share one wave
         uint32_t pixel = w.slot_pixel ? w.slot_pixel[ps] : ps;
         PtPath p;
-        pt_path_init(&p, f.cam, f.seed, pixel, f.sample + k, f.width, f.height);
+        pt_path_init(&p, f.cam, f.seed, pixel, f.sample + k, f.width, f.height, f.flags);
         w.ray_o[s] = make_float4(p.o.x, p.o.y, p.o.z, 0.0f);
         w.ray_d[s] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(0u));
         w.beta[s] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel));

@@ -14,6 +14,7 @@
 #define PT_FLAG_NO_NEE 2u
 #define PT_FLAG_NO_BSDF_EMISSION 4u
 #define PT_FLAG_MATERIAL_SORT 8u
+#define PT_FLAG_SOBOL_JITTER 16u
 
 struct PtShadeConsts {
     const PtLight* lights;
@@ -55,9 +56,37 @@ PT_HD void pt_camera_ray(const PtCamera& cam, uint32_t px, uint32_t py, uint32_t
     *d = pt_normalize(dir);
 }
 
-PT_HD void pt_path_init(PtPath* p, const PtCamera& cam, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t width, uint32_t height) {
+// Sub-pixel positions from the Sobol (0,2)-sequence: dimension 0 is the radical inverse in base 2 (van der Corput), dimension 1 the
+// second Sobol dimension (direction numbers v_k = v_{k-1} ^ (v_{k-1} >> 1), i.e. the Pascal-triangle generator matrix), each XOR-
+// scrambled with a per-pixel key (random digit scrambling keeps the (0,2) stratification: any 2^k consecutive samples starting at
+// a multiple of 2^k put one point in every elementary interval of area 2^-k).  Integer-only, so both machines agree to the bit.
+PT_HD uint32_t pt_reverse_bits32(uint32_t x) {
+    x = (x << 16) | (x >> 16);
+    x = ((x & 0x00ff00ffu) << 8) | ((x & 0xff00ff00u) >> 8);
+    x = ((x & 0x0f0f0f0fu) << 4) | ((x & 0xf0f0f0f0u) >> 4);
+    x = ((x & 0x33333333u) << 2) | ((x & 0xccccccccu) >> 2);
+    x = ((x & 0x55555555u) << 1) | ((x & 0xaaaaaaaau) >> 1);
+    return x;
+}
+PT_HD uint32_t pt_sobol2(uint32_t i) {
+    uint32_t r = 0;
+    for (uint32_t v = 0x80000000u; i; i >>= 1, v ^= v >> 1)
+        if (i & 1u) r ^= v;
+    return r;
+}
+PT_HD void pt_sobol02(uint32_t sample, uint32_t key0, uint32_t key1, float* x, float* y) {
+    *x = (float)((pt_reverse_bits32(sample) ^ key0) >> 8) * 5.9604644775390625e-08f;
+    *y = (float)((pt_sobol2(sample) ^ key1) >> 8) * 5.9604644775390625e-08f;
+}
+
+PT_HD void pt_path_init(PtPath* p, const PtCamera& cam, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t width, uint32_t height,
+                        uint32_t flags = 0) {
     p->rng = pt_rng_for(seed, pixel, sample);
-    float jx = pt_rng_f(&p->rng), jy = pt_rng_f(&p->rng);
+    float jx = pt_rng_f(&p->rng), jy = pt_rng_f(&p->rng);     // always drawn: the stream layout does not depend on the flag
+    if (flags & PT_FLAG_SOBOL_JITTER) {
+        uint64_t k = pt_mix64(seed ^ pt_mix64(0x50b01ull + pixel));
+        pt_sobol02(sample, (uint32_t)k, (uint32_t)(k >> 32), &jx, &jy);
+    }
     pt_camera_ray(cam, pixel % width, pixel / width, width, height, jx, jy, &p->o, &p->d);
     p->beta = pt_mk(1.0f, 1.0f, 1.0f);
     p->L = pt_mk(0.0f, 0.0f, 0.0f);

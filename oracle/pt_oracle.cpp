@@ -583,7 +583,7 @@ void orc_render(void* p, uint32_t width, uint32_t height, uint64_t seed, uint32_
             if (!owns_pixel(x, y, rank, count, tile)) continue;
             for (uint32_t smp = s0; smp < s0 + ns; ++smp) {
                 PtPath path;
-                pt_path_init(&path, s.cam, seed, (uint32_t)pix, smp, width, height);
+                pt_path_init(&path, s.cam, seed, (uint32_t)pix, smp, width, height, flags);
                 for (;;) {
                     ++ext;
                     Hit h = brute ? trace_brute(s, path.o, path.d, 0.0f, INFINITY, false, &c) : trace_bvh(s, path.o, path.d, 0.0f, INFINITY, false, &c);
@@ -633,6 +633,7 @@ uint32_t orc_pcg_raw(uint64_t initstate, uint64_t initseq, uint32_t n, uint32_t*
     return n;
 }
 uint64_t orc_morton(const float* c, const float* lo, const float* inv) { return pt_morton63(pt_mk(c[0], c[1], c[2]), pt_mk(lo[0], lo[1], lo[2]), pt_mk(inv[0], inv[1], inv[2])); }
+void orc_sobol02(uint32_t sample, uint32_t k0, uint32_t k1, float* x, float* y) { pt_sobol02(sample, k0, k1, x, y); }
 int orc_hw_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         L.orc_pcg_raw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
         L.orc_morton.restype = C.c_uint64
         L.orc_morton.argtypes = [C.c_void_p] * 3
+        L.orc_sobol02.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.orc_hw_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -195,6 +196,10 @@ def pcg(seed, pixel, sample, n):
 
 def pcg_raw(initstate, initseq, n):
     out = np.zeros(n, np.uint32); lib().orc_pcg_raw(initstate, initseq, n, _p(out)); return out
+
+
+def sobol02(sample, k0=0, k1=0):
+    x = C.c_float(); y = C.c_float(); lib().orc_sobol02(sample, k0, k1, C.byref(x), C.byref(y)); return x.value, y.value
 
 
 def hw_threads():

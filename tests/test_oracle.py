@@ -350,3 +350,29 @@ def test_bsdf_matches_independent_float64_formula():
             f, pdf = orc.bsdf_eval(mat, v[0].astype(np.float32), v[1].astype(np.float32))
             fr, pr = ref(mat, v[0].astype(np.float32).astype(np.float64), v[1].astype(np.float32).astype(np.float64))
             assert np.allclose(f, fr, rtol=2e-3, atol=1e-6) and abs(pdf - pr) <= 2e-3 * max(pr, 1e-3), (mat, f, fr, pdf, pr)
+
+
+def test_sobol02_is_a_02_sequence_and_known_values():
+    """Known first points of the (0,2)-sequence (van der Corput base 2; second Sobol dimension 0, .5, .25, .75, .125 ...  and
+    0, .5, .75, .25, .625 ...), and the defining stratification: every aligned block of 2^k samples hits each elementary interval
+    of area 2^-k exactly once, with and without XOR scrambling."""
+    pts = np.asarray([orc.sobol02(i) for i in range(8)])
+    assert np.allclose(pts[:, 0], [0, .5, .25, .75, .125, .625, .375, .875])
+    assert np.allclose(pts[:, 1], [0, .5, .75, .25, .625, .125, .375, .875])
+    for k0, k1 in ((0, 0), (0x9E3779B9, 0x7F4A7C15)):
+        for k in (4, 6):
+            n = 1 << k
+            for start in (0, n, 5 * n):
+                p = np.asarray([orc.sobol02(start + i, k0, k1) for i in range(n)])
+                for a in range(k + 1):                       # grid 2^a x 2^(k-a)
+                    cells = np.floor(p[:, 0] * (1 << a)).astype(int) * (1 << (k - a)) + np.floor(p[:, 1] * (1 << (k - a))).astype(int)
+                    assert len(set(cells.tolist())) == n, (k0, k, start, a)
+
+
+def test_sobol_jitter_lowers_pixel_variance_and_keeps_the_mean():
+    sc = scenes.cornell_box(24, 24)
+    o = OracleScene(sc)
+    spp = 64
+    a = o.render(24, 24, 3, 0, spp, 2, flags=0)[..., :3] / spp
+    b = o.render(24, 24, 3, 0, spp, 2, flags=16)[..., :3] / spp
+    assert abs(a.mean() - b.mean()) / a.mean() < 0.05 and not np.array_equal(a, b)
