@@ -27,7 +27,14 @@ def build(force: bool = False) -> str:
     newest = max([os.path.getmtime(src)] + [os.path.getmtime(os.path.join(hdr_dir, h)) for h in
                                             ("pt_math.h", "pt_layout.h", "pt_shading.h", "pt_host_shared.h") if os.path.exists(os.path.join(hdr_dir, h))])
     if force or not os.path.exists(so) or os.path.getmtime(so) < newest:
-        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+        import fcntl
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:      # concurrent test workers / ranks: one builder at a time
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or not os.path.exists(so) or os.path.getmtime(so) < newest:
+                    subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return so
 
 
