@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(PT_SCAN_THREADS) k_scan_add(uint32_t* out, uin
 // Per pass: per-tile digit histogram -> exclusive scan over [digit][tile] -> stable scatter with a tile-local sort.
 // ---------------------------------------------------------------------------------------------------
 #define PT_RS_THREADS 256
-#define PT_RS_ROUNDS 16
+#define PT_RS_ROUNDS 4
 #define PT_RS_TILE (PT_RS_THREADS * PT_RS_ROUNDS)
 
 __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_hist(const uint64_t* keys, uint32_t n, int shift, uint32_t* tile_hist, uint32_t num_tiles) {
