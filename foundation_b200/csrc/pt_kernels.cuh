@@ -297,19 +297,21 @@ __device__ __forceinline__ PtBox pt_ldcg_box(const PtBox* p) {
 __global__ void __launch_bounds__(256) k_refit(PtBvh2 b, const PtBox* prim_box, const uint32_t* order, uint32_t* flags) {
     const uint32_t n = b.n;
     for (uint32_t j = pt_gtid(); j < n; j += pt_gsize()) {
-        b.box[n - 1 + j] = prim_box[order[j]];
+        PtBox mine = prim_box[order[j]];          // the box of the subtree this thread is carrying upwards stays in registers
+        uint32_t me = n - 1 + j;
+        b.box[me] = mine;
         if (n == 1) return;
-        uint32_t cur = b.parent[n - 1 + j];
         for (;;) {
-            __threadfence();
-            if (atomicAdd(&flags[cur], 1u) == 0u) break;
-            PtBox l = pt_ldcg_box(&b.box[b.left[cur]]), r = pt_ldcg_box(&b.box[b.right[cur]]);
-            PtBox u;
-            u.lox = pt_min(l.lox, r.lox); u.loy = pt_min(l.loy, r.loy); u.loz = pt_min(l.loz, r.loz);
-            u.hix = pt_max(l.hix, r.hix); u.hiy = pt_max(l.hiy, r.hiy); u.hiz = pt_max(l.hiz, r.hiz);
-            b.box[cur] = u;
+            uint32_t cur = b.parent[me];
+            __threadfence();                       // publish box[me] before announcing arrival
+            if (atomicAdd(&flags[cur], 1u) == 0u) break;   // first arriver leaves; the second one owns the parent
+            uint32_t l = b.left[cur];
+            PtBox s = pt_ldcg_box(&b.box[l == me ? b.right[cur] : l]);     // only the sibling has to be read back (L2, not L1)
+            mine.lox = pt_min(mine.lox, s.lox); mine.loy = pt_min(mine.loy, s.loy); mine.loz = pt_min(mine.loz, s.loz);
+            mine.hix = pt_max(mine.hix, s.hix); mine.hiy = pt_max(mine.hiy, s.hiy); mine.hiz = pt_max(mine.hiz, s.hiz);
+            b.box[cur] = mine;
             if (cur == 0) break;
-            cur = b.parent[cur];
+            me = cur;
         }
     }
 }
