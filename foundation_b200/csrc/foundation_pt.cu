@@ -565,11 +565,8 @@ int32_t foundation_pt_instances_set(foundation_pt_context* ctx, const foundation
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
     if (!instances || count == 0) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "instances NULL or empty");
     PT_TRY
-    for (uint32_t i = 0; i < count; ++i) {
+    for (uint32_t i = 0; i < count; ++i)      // singular transforms are detected on the device at scene_commit (ERR_ARGUMENT there)
         if (instances[i].mesh_id >= ctx->meshes.size()) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "instances_set: mesh_id out of range");
-        float w2o[12];
-        if (!pt_invert_affine(instances[i].transform, w2o)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "instances_set: singular transform");
-    }
     ctx->insts.assign(instances, instances + count);
     ctx->has_insts = true; ctx->committed = false;
     return FOUNDATION_PT_OK;
@@ -595,7 +592,6 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
     uint64_t total_tris = 0, eff_tris = 0, total_nodes = 0;
     for (auto& m : ctx->meshes) { total_tris += m.ntris; total_nodes += m.num_nodes; }
     ctx->mesh_info.assign(ctx->meshes.size(), PtMeshInfo{});
-    std::vector<PtInstance> rec;
     if (ctx->two_level) {
         if (!ctx->has_insts) {
             ctx->insts.resize(ctx->meshes.size());
@@ -607,13 +603,7 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
         }
         uint32_t ni = (uint32_t)ctx->insts.size();
         ctx->num_inst = ni;
-        rec.resize(ni);
-        for (uint32_t i = 0; i < ni; ++i) {
-            memcpy(rec[i].o2w, ctx->insts[i].transform, 48);
-            pt_invert_affine(rec[i].o2w, rec[i].w2o);
-            rec[i].mesh_id = ctx->insts[i].mesh_id; rec[i].inst_id = i; rec[i].node_base = rec[i].tri_base = 0;
-            eff_tris += ctx->meshes[rec[i].mesh_id].ntris;
-        }
+        for (uint32_t i = 0; i < ni; ++i) eff_tris += ctx->meshes[ctx->insts[i].mesh_id].ntris;
         for (size_t k = 0; k < ctx->meshes.size(); ++k) {
             memcpy(ctx->mesh_info[k].lo, ctx->meshes[k].lo, 12); memcpy(ctx->mesh_info[k].hi, ctx->meshes[k].hi, 12);
             ctx->mesh_info[k].pad = ctx->meshes[k].pad; ctx->mesh_info[k].ntris = ctx->meshes[k].ntris; ctx->mesh_info[k].nnodes = ctx->meshes[k].num_nodes;
@@ -624,7 +614,17 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
             blas_nodes += ctx->meshes[k].num_nodes; blas_tris += ctx->meshes[k].ntris;
         }
         PT_CK(ctx->d_inst_in.alloc((size_t)ni * sizeof(PtInstance))); PT_CK(ctx->d_mesh_info.alloc(ctx->mesh_info.size() * sizeof(PtMeshInfo)));
-        PT_CK(cudaMemcpyAsync(ctx->d_inst_in.p, rec.data(), (size_t)ni * sizeof(PtInstance), cudaMemcpyHostToDevice, ctx->stream));
+        {   // instance records (inverse transforms in double) are derived on the device from the raw 64-byte ABI records
+            int32_t rcs = ensure_status(ctx);
+            if (rcs) return rcs;
+            DevBuf d_raw; PT_CK(d_raw.alloc((size_t)ni * sizeof(foundation_pt_instance)));
+            PT_CK(cudaMemcpyAsync(d_raw.p, ctx->insts.data(), (size_t)ni * sizeof(foundation_pt_instance), cudaMemcpyHostToDevice, ctx->stream));
+            PT_LAUNCH(ctx, k_inst_prepare, grid_for(ctx, ni, 256, 8), 256, d_raw.as<PtInstanceIn>(), ni, ctx->d_inst_in.as<PtInstance>(), ctx->d_status.as<uint32_t>());
+            uint32_t st = 0;
+            PT_CK(cudaMemcpyAsync(&st, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PT_CK(cudaStreamSynchronize(ctx->stream));
+            if (st & 2u) { cudaMemsetAsync(ctx->d_status.p, 0, 4, ctx->stream); return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "scene_commit: singular instance transform"); }
+        }
         PT_CK(cudaMemcpyAsync(ctx->d_mesh_info.p, ctx->mesh_info.data(), ctx->mesh_info.size() * sizeof(PtMeshInfo), cudaMemcpyHostToDevice, ctx->stream));
         // A6: TLAS = the same LBVH -> BVH8 pipeline over instance world boxes, one instance per leaf slot
         DevBuf prim_box, bounds, bp, keys, vals;
@@ -714,7 +714,10 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
                 lights.push_back(l);
             }
         };
-        if (ctx->two_level) for (uint32_t i = 0; i < ctx->num_inst; ++i) add_mesh_lights(rec[i].mesh_id, rec[i].o2w);
+        if (ctx->two_level) {
+            for (uint32_t i = 0; i < ctx->num_inst; ++i)
+                if (!em_tris[ctx->insts[i].mesh_id].empty()) add_mesh_lights(ctx->insts[i].mesh_id, ctx->insts[i].transform);
+        }
         else add_mesh_lights(0, nullptr);
     }
     ctx->num_lights = (uint32_t)lights.size();

@@ -48,8 +48,9 @@ static inline bool pt_camera_derive(const float* view, const float* proj, PtCame
     return true;
 }
 
-// world->object rows from object->world rows (affine 3x4), in double
-static inline bool pt_invert_affine(const float* o2w, float* w2o) {
+// world->object rows from object->world rows (affine 3x4), in double.  __host__ __device__: IEEE double + - * / in a fixed order, no
+// contraction on either side, so the device (k_inst_prepare) and the oracle (host) produce the same floats.
+PT_HD bool pt_invert_affine(const float* o2w, float* w2o) {
     double a = o2w[0], b = o2w[1], c = o2w[2], d = o2w[4], e = o2w[5], f = o2w[6], g = o2w[8], h = o2w[9], i = o2w[10];
     double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
     double det = a * A + b * B + c * C;

@@ -378,6 +378,17 @@ __global__ void __launch_bounds__(256) k_emissive_list(const uint32_t* mat, uint
 // A6: TLAS inputs — world boxes of instances, and the leaf-ordered instance records
 // ---------------------------------------------------------------------------------------------------
 struct PtMeshInfo { float lo[3], hi[3]; float pad; uint32_t node_base, tri_base, ntris, nnodes; };
+// caller's instance list (64-byte ABI records: mesh id, 3 pad words, 12 floats) -> device instance records with the inverse transform
+struct PtInstanceIn { uint32_t mesh_id, r0, r1, r2; float o2w[12]; };
+__global__ void __launch_bounds__(256) k_inst_prepare(const PtInstanceIn* in, uint32_t n, PtInstance* out, uint32_t* status) {
+    for (uint32_t i = pt_gtid(); i < n; i += pt_gsize()) {
+        PtInstance r;
+        for (int k = 0; k < 12; ++k) r.o2w[k] = in[i].o2w[k];
+        if (!pt_invert_affine(r.o2w, r.w2o)) atomicOr(status, 2u);
+        r.node_base = 0; r.tri_base = 0; r.mesh_id = in[i].mesh_id; r.inst_id = i;
+        out[i] = r;
+    }
+}
 __global__ void __launch_bounds__(256) k_inst_boxes(const PtInstance* inst, uint32_t n, const PtMeshInfo* meshes, PtBox* prim_box, uint32_t* bounds) {
     PtOrdBounds ob; pt_ord_init(ob);
     for (uint32_t i = pt_gtid(); i < n; i += pt_gsize()) {

@@ -150,7 +150,8 @@ FOUNDATION_PT_API int32_t foundation_pt_materials_set(foundation_pt_context* ctx
 FOUNDATION_PT_API int32_t foundation_pt_mesh_create(foundation_pt_context* ctx, const void* positions, size_t pos_stride_bytes,
                                                     uint32_t num_vertices, const void* indices, uint32_t index_format,
                                                     uint32_t num_triangles, const uint32_t* material_ids, uint32_t* out_mesh_id);
-/* Optional.  Without it every mesh is instanced once with the identity transform. */
+/* Optional.  Without it every mesh is instanced once with the identity transform.  A singular transform is reported by the
+ * following scene_commit (FOUNDATION_PT_ERR_ARGUMENT): the inverse matrices are computed on the device. */
 FOUNDATION_PT_API int32_t foundation_pt_instances_set(foundation_pt_context* ctx, const foundation_pt_instance* instances, uint32_t count);
 /* Builds every BLAS (Morton LBVH -> BVH8) and the TLAS on the device.  stats may be NULL. */
 FOUNDATION_PT_API int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_build_stats* stats);

@@ -162,6 +162,13 @@ def test_error_behaviour(gpu):
     t.scene_commit()
     with pytest.raises(pt.FoundationPtError):
         t.render(0, 1, 1)            # camera not set
+    bad = np.zeros(1, scenes.INSTANCE_DTYPE)                 # singular instance transform: reported by the commit that follows
+    t.instances_set(bad)
+    with pytest.raises(pt.FoundationPtError) as e:
+        t.scene_commit()
+    assert e.value.status == pt.ERR_ARGUMENT and "singular" in str(e.value)
+    ident = np.zeros(1, scenes.INSTANCE_DTYPE); ident["transform"][0] = (1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0)
+    t.instances_set(ident); t.scene_commit()
     # single-triangle scene, empty ray set, degenerate rays
     hits, _ = t.trace_closest(np.zeros(0, scenes.RAY_DTYPE))
     assert len(hits) == 0
