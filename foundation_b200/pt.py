@@ -235,6 +235,15 @@ class PathTracer:
         self._check(self._lib.foundation_pt_resolve_rgba8(self._ctx, _p(out), out.nbytes))
         return out
 
+    # -- image output: linear mean radiance as PFM, the presented RGBA8 frame as PNG
+    def save_pfm(self, path: str):
+        from . import imageio
+        imageio.write_pfm(path, imageio.radiance_from_accum(self.read_accum()))
+
+    def save_png(self, path: str):
+        from . import imageio
+        imageio.write_png(path, self.resolve_rgba8())
+
     def accum_device_ptr(self):
         ptr = C.c_void_p(); size = C.c_size_t()
         self._check(self._lib.foundation_pt_accum_device_ptr(self._ctx, C.byref(ptr), C.byref(size)))

@@ -1,7 +1,7 @@
 // Editor.cpp — headless stand-in for the reference's only caller of the renderer (src/Editor/Editor.cpp:13-44):
 // construct the allocator, the device handle and the Renderer, call Draw() in a loop, report allocator bytes at exit.
 // There is no window on the GPU box, so the loop runs a fixed number of frames and writes the result to disk instead of presenting.
-//   usage: foundation_editor <scene.fpts> <frames> <samples_per_draw> <max_bounces> [out.raw] [out.ppm] [spin_degrees_per_frame]
+//   usage: foundation_editor <scene.fpts> <frames> <samples_per_draw> <max_bounces> [accum.raw] [out.ppm] [spin_degrees_per_frame] [out.pfm]
 // With a spin angle every frame rotates all instances about +Z by frame * angle before drawing, like the reference's per-frame model
 // matrix (src/Renderer/Renderer.cpp:373): TLAS-only rebuild + accumulation restart each Draw().
 #include <atomic>
@@ -49,7 +49,7 @@ CountingAllocator g_Allocator;
 }  // namespace
 
 int main(int argc, char** argv) {
-    if (argc < 5) { std::fprintf(stderr, "usage: %s scene.fpts frames samples_per_draw max_bounces [out.pfm] [out.ppm]\n", argv[0]); return 2; }
+    if (argc < 5) { std::fprintf(stderr, "usage: %s scene.fpts frames samples_per_draw max_bounces [accum.raw] [out.ppm] [spin] [out.pfm]\n", argv[0]); return 2; }
     Renderer::SceneDesc scene; std::string err;
     if (!scene.Load(argv[1], &err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 2; }
     int frames = std::atoi(argv[2]); uint32_t spd = (uint32_t)std::atoi(argv[3]), bounces = (uint32_t)std::atoi(argv[4]);
@@ -76,10 +76,27 @@ int main(int argc, char** argv) {
         foundation_pt_build_stats bs = renderer.BuildStats();
         std::printf("frames=%d spp=%u ms=%.3f spp_per_s=%.2f tris=%llu nodes8=%llu build_ms=%.2f\n", frames, renderer.SamplesDone(), ms,
                     renderer.SamplesDone() / (ms * 1e-3), (unsigned long long)bs.num_triangles, (unsigned long long)bs.num_nodes8, bs.build_ms);
-        if (argc > 5) {   // linear radiance sum (PFM is bottom-up: write rows reversed), plus the sample count in the alpha of the raw dump
+        if (argc > 5) {   // the float4 accumulation buffer as is: radiance sum in rgb, sample count in alpha
             std::vector<float> acc; renderer.ReadAccum(&acc);
             FILE* f = std::fopen(argv[5], "wb");
             if (f) { std::fwrite(acc.data(), sizeof(float), acc.size(), f); std::fclose(f); }   // raw float4 dump (row-major from the top-left)
+        }
+        if (argc > 8) {   // mean linear radiance as a colour PFM: little-endian (scale -1.0), rows bottom-up
+            std::vector<float> acc; renderer.ReadAccum(&acc);
+            FILE* f = std::fopen(argv[8], "wb");
+            if (f) {
+                const uint32_t w = renderer.Width(), h = renderer.Height();
+                std::fprintf(f, "PF\n%u %u\n-1.0\n", w, h);
+                std::vector<float> row(3 * (size_t)w);
+                for (uint32_t y = h; y-- > 0;) {
+                    for (uint32_t x = 0; x < w; ++x) {
+                        const float* a = &acc[4 * ((size_t)y * w + x)];
+                        for (int c = 0; c < 3; ++c) row[3 * x + c] = a[3] > 0.0f ? a[c] / a[3] : 0.0f;
+                    }
+                    std::fwrite(row.data(), sizeof(float), row.size(), f);
+                }
+                std::fclose(f);
+            }
         }
         if (argc > 6) {
             FILE* f = std::fopen(argv[6], "wb");

@@ -190,12 +190,27 @@ def test_cpp_renderer_host_draw_loop_matches_oracle(gpu, tmp_path):
     sc = SMALL_SCENES["cornell"]()
     path = str(tmp_path / "cornell.fpts"); raw = str(tmp_path / "acc.raw"); ppm = str(tmp_path / "out.ppm")
     scenes.save_scene(sc, path)
-    out = subprocess.run([os.path.join(rdir, "foundation_editor"), path, "3", "2", "4", raw, ppm], check=True, capture_output=True, text=True).stdout
+    pfm = str(tmp_path / "out.pfm")
+    out = subprocess.run([os.path.join(rdir, "foundation_editor"), path, "3", "2", "4", raw, ppm, "0", pfm], check=True, capture_output=True, text=True).stdout
     assert "spp=6" in out and "Memory Used: 0 bytes" in out, out          # three Draw() calls of two samples; nothing leaked through Core::Allocator
     acc = np.fromfile(raw, np.float32).reshape(sc.height, sc.width, 4)
     o = OracleScene(sc).render(sc.width, sc.height, 7, 0, 6, 4, background=sc.background)
     assert np.array_equal(acc, o)
     assert os.path.getsize(ppm) > sc.width * sc.height * 3
+    from foundation_b200 import imageio
+    assert np.array_equal(imageio.read_pfm(pfm), imageio.radiance_from_accum(o))   # the C++ writer and the Python resolve agree bit for bit
+
+
+def test_image_output_pfm_png(gpu, tmp_path):
+    """save_pfm / save_png write what read_accum / resolve_rgba8 return."""
+    from foundation_b200 import imageio
+    sc = SMALL_SCENES["cornell"]()
+    with pt.PathTracer(sc.width, sc.height, seed=3) as tr:
+        tr.load(sc)
+        tr.render(0, 2, 3)
+        tr.save_pfm(str(tmp_path / "a.pfm")); tr.save_png(str(tmp_path / "a.png"))
+        assert np.array_equal(imageio.read_pfm(str(tmp_path / "a.pfm")), imageio.radiance_from_accum(tr.read_accum()))
+        assert np.array_equal(imageio.read_png(str(tmp_path / "a.png")), tr.resolve_rgba8())
 
 
 @pytest.mark.parametrize("leaf", [1, 2, 3])
