@@ -67,11 +67,22 @@ struct PtCamera { float eye[3], d0[3], dx[3], dy[3]; };
 #define PT_PAD_REL 1.9073486328125e-06f  // 2^-19: child boxes are padded by this x max |coordinate| before quantisation
 #define PT_MAX_LEAF 1   // default triangles per leaf slot (the format allows 3): measured 7-9 % faster than 3 on configs 2-4, 1.9x on Cornell:
                        // every extra triangle of a leaf is one more random 64-byte DRAM fetch, a tighter box avoids it
-// Ray-dependent slack of the slab test: every plane distance t = q*a + b is widened by PT_SLAB_EPS * (255 |a| + |b|), a bound on
-// the rounding error of that expression (3 ulp of the larger term, x2.7 margin).  The build-time pad covers coordinates near the
-// mesh; this covers rays whose origin is far away compared with the mesh (instanced BLAS in object space, distant cameras), where
-// the error of (p - o) * idir grows with the distance.  2^-21.
+// Ray-dependent slack of the slab test.  A plane distance is evaluated as t = fma(QBIAS + q, a, c) with a = scale * idir,
+// b = (p - o) * idir and c = b - QBIAS * a (the bias lets the byte q be turned into a float with one byte permute, pt_qfloat).  That is
+// five roundings, each at most 2^-24 of (|b| + (QBIAS + 255) |a|); every plane is widened by PT_SLAB_EPS = 2^-21 times that bound
+// (x1.6 margin): 1.6 % of one quantisation step plus 2^-21 of the distance term.  The build-time pad covers coordinates near the mesh;
+// this covers rays whose origin is far away compared with the mesh (instanced BLAS in object space, distant cameras), where the error
+// of (p - o) * idir grows with the distance.
 #define PT_SLAB_EPS 4.76837158203125e-07f
+#define PT_QBIAS 32768.0f
+#define PT_QBIAS_BITS 0x47000000u
+#define PT_SLAB_QMAX 33023.0f   // QBIAS + 255
+
+// relative costs of the collapse plan (pt_build.h): visiting a wide node / testing one triangle, per unit of surface area
+#define PT_COST_NODE 1.0f
+#ifndef PT_COST_TRI
+#define PT_COST_TRI 0.3f
+#endif
 
 // ---- quantisation rules -------------------------------------------------------------------------
 // biased exponent e such that 255 * 2^(e-127) >= extent (smallest such e, clamped to [1,253])

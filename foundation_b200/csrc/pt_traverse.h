@@ -43,6 +43,9 @@ struct PtSceneView {
     const PtU4* instances;    // PtInstance records in TLAS leaf order, 7 x 16 B each (two_level only)
     uint32_t tlas_base;       // index of the TLAS root in `nodes` (the TLAS sits after the BLAS so it can be rebuilt alone)
     uint32_t zero;            // always 0, but only known at run time: see pt_test_tri_words
+    uint32_t qbias = PT_QBIAS_BITS;   // float bits of PT_QBIAS as run-time data: kept in ONE register it serves all 48 byte permutes of a node
+                                      // test with immediate selectors (as a literal, ptxas puts it in the immediate slot and moves the selectors
+                                      // through registers instead: +36 instructions per node)
 };
 
 struct PtRayCtx {
@@ -61,18 +64,27 @@ PT_HD void pt_ray_ctx(PtRayCtx* c, pt_v3 o, pt_v3 d) {
 }
 
 PT_HD uint32_t pt_byte(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
+// byte i of w as the float PT_QBIAS + q: q lands in mantissa bits 8..15 of 2^15 (0x47000000), exact for q in 0..255
+#if defined(__CUDA_ARCH__)
+PT_HD float pt_qfloat(uint32_t w, int i, uint32_t qbias) { return __uint_as_float(__byte_perm(w, qbias, 0x7404u | ((uint32_t)i << 4))); }
+#else
+PT_HD float pt_qfloat(uint32_t w, int i, uint32_t qbias) { return pt_u2f(qbias | (pt_byte(w, i) << 8)); }
+#endif
 
 // Intersects the 8 quantised child boxes of one node.  Returns the hit mask: bits 24..31 = internal
 // children that are hit, at position 24 + (slot ^ oct_inv); bits 0..23 = triangles of leaf slots that are hit.
 PT_HD uint32_t pt_node_hits(const PtU4& n0, const PtU4& n1, const PtU4& n2, const PtU4& n3, const PtU4& n4, const PtRayCtx& r, float tmin,
-                            float tbest) {
+                            float tbest, uint32_t qbias) {
     float sx = pt_u2f((n0.w & 0xffu) << 23), sy = pt_u2f(((n0.w >> 8) & 0xffu) << 23), sz = pt_u2f(((n0.w >> 16) & 0xffu) << 23);
     float ax = sx * r.idir.x, ay = sy * r.idir.y, az = sz * r.idir.z;
     float bx = (pt_u2f(n0.x) - r.o.x) * r.idir.x, by = (pt_u2f(n0.y) - r.o.y) * r.idir.y, bz = (pt_u2f(n0.z) - r.o.z) * r.idir.z;
-    // near planes move towards the origin, far planes away from it, by the rounding-error bound of q*a + b (see PT_SLAB_EPS)
-    float ex = pt_fma(pt_abs(ax), 255.0f, pt_abs(bx)) * PT_SLAB_EPS, ey = pt_fma(pt_abs(ay), 255.0f, pt_abs(by)) * PT_SLAB_EPS,
-          ez = pt_fma(pt_abs(az), 255.0f, pt_abs(bz)) * PT_SLAB_EPS;
-    float bnx = bx - ex, bny = by - ey, bnz = bz - ez, bfx = bx + ex, bfy = by + ey, bfz = bz + ez;
+    // near planes move towards the origin, far planes away from it, by the rounding-error bound of the plane distance (see PT_SLAB_EPS).
+    // The quantised byte q enters the fma as the float PT_QBIAS + q (pt_qfloat: one byte permute, no int->float conversion, which
+    // is a quarter-rate XU instruction and was the busiest pipe of the kernel); the bias is folded into the constant term.
+    float ex = pt_fma(pt_abs(ax), PT_SLAB_QMAX, pt_abs(bx)) * PT_SLAB_EPS, ey = pt_fma(pt_abs(ay), PT_SLAB_QMAX, pt_abs(by)) * PT_SLAB_EPS,
+          ez = pt_fma(pt_abs(az), PT_SLAB_QMAX, pt_abs(bz)) * PT_SLAB_EPS;
+    float cx = pt_fma(-PT_QBIAS, ax, bx), cy = pt_fma(-PT_QBIAS, ay, by), cz = pt_fma(-PT_QBIAS, az, bz);
+    float bnx = cx - ex, bny = cy - ey, bnz = cz - ez, bfx = cx + ex, bfy = cy + ey, bfz = cz + ez;
     bool negx = !(r.oct_inv & 4u), negy = !(r.oct_inv & 2u), negz = !(r.oct_inv & 1u);
     uint32_t mask = 0;
     const uint32_t oct4 = r.oct_inv * 0x01010101u;
@@ -95,9 +107,9 @@ PT_HD uint32_t pt_node_hits(const PtU4& n0, const PtU4& n1, const PtU4& n2, cons
 #pragma unroll
 #endif
         for (int j = 0; j < 4; ++j) {
-            float tnx = pt_fma((float)pt_byte(nx, j), ax, bnx), tfx = pt_fma((float)pt_byte(fx, j), ax, bfx);
-            float tny = pt_fma((float)pt_byte(ny, j), ay, bny), tfy = pt_fma((float)pt_byte(fy, j), ay, bfy);
-            float tnz = pt_fma((float)pt_byte(nz, j), az, bnz), tfz = pt_fma((float)pt_byte(fz, j), az, bfz);
+            float tnx = pt_fma(pt_qfloat(nx, j, qbias), ax, bnx), tfx = pt_fma(pt_qfloat(fx, j, qbias), ax, bfx);
+            float tny = pt_fma(pt_qfloat(ny, j, qbias), ay, bny), tfy = pt_fma(pt_qfloat(fy, j, qbias), ay, bfy);
+            float tnz = pt_fma(pt_qfloat(nz, j, qbias), az, bnz), tfz = pt_fma(pt_qfloat(fz, j, qbias), az, bfz);
             float tn = pt_fmax(pt_fmax(tnx, tny), pt_fmax(tnz, tmin));
             float tf = pt_fmin(pt_fmin(tfx, tfy), pt_fmin(tfz, tbest));
             uint32_t sel = (tn <= tf) ? 0xffffffffu : 0u;
@@ -237,7 +249,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
     }
     if (do_node) {   // children are culled against the best hit INCLUDING the triangle tested just above
         cnt.node();
-        uint32_t hits = pt_node_hits(n0, n1, n2, n3, n4, s->r, s->tmin, best->t);
+        uint32_t hits = pt_node_hits(n0, n1, n2, n3, n4, s->r, s->tmin, best->t, sc.qbias);
         s->ng.x = n1.x; s->ng.y = (hits & 0xff000000u) | (n0.w >> 24);
         s->tg.x = n1.y; s->tg.y = hits & 0x00ffffffu;
     }

@@ -107,6 +107,70 @@ void build_lbvh(const std::vector<Box3>& pbox, const std::vector<pt_v3>& cent, c
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Collapse plan: the surface-area-cost dynamic programme of Ylitie, Karras, Laine (HPG 2017, section 3.1).
+// cost[ref][i-1], i = 1..7 = cheapest way to represent the subtree of BVH2 node `ref` as at most i children
+// of a wide node; plan[ref][j-2], j = 2..8 = how many of j slots go to the left child (low nibble), bit 7 =
+// "j-1 slots are as cheap"; plan[ref][7] = 1 when the subtree is one leaf slot.
+// ---------------------------------------------------------------------------------------------------
+struct CollapsePlan { std::vector<float> cost; std::vector<uint8_t> plan; };
+
+static inline float ref_area(const Bvh2& b, uint32_t ref) {
+    const Box3& x = b.box[ref];
+    return pt_box_area(x.lo[0], x.lo[1], x.lo[2], x.hi[0], x.hi[1], x.hi[2]);
+}
+static inline float plan_cost(const Bvh2& b, const CollapsePlan& pl, uint32_t ref, int i) {   // i = 1..7
+    return ref >= b.n - 1 ? ref_area(b, ref) * PT_COST_TRI : pl.cost[(size_t)ref * 7 + (i - 1)];
+}
+void plan_collapse(const Bvh2& b, uint32_t max_leaf, CollapsePlan* pl) {
+    uint32_t n = b.n;
+    if (n < 2) return;
+    pl->cost.assign((size_t)(n - 1) * 7, 0.0f); pl->plan.assign((size_t)(n - 1) * 8, 0);
+    std::vector<uint32_t> order; order.reserve(n - 1);
+    std::vector<uint32_t> st{0};
+    while (!st.empty()) {   // parents before children; processed in reverse
+        uint32_t r = st.back(); st.pop_back(); order.push_back(r);
+        if (b.left[r] < n - 1) st.push_back(b.left[r]);
+        if (b.right[r] < n - 1) st.push_back(b.right[r]);
+    }
+    for (size_t q = order.size(); q-- > 0;) {
+        uint32_t r = order[q], L = b.left[r], R = b.right[r];
+        float cl[8], cr[8], D[9];
+        for (int i = 1; i <= 7; ++i) { cl[i] = plan_cost(b, *pl, L, i); cr[i] = plan_cost(b, *pl, R, i); }
+        uint8_t* P = &pl->plan[(size_t)r * 8];
+        for (int j = 2; j <= 8; ++j) {
+            int bk = 1; float bc = cl[1] + cr[j - 1];
+            for (int k = 2; k < j; ++k) { float c = cl[k] + cr[j - k]; if (c < bc) { bc = c; bk = k; } }
+            D[j] = bc; P[j - 2] = (uint8_t)bk;
+        }
+        float A = ref_area(b, r);
+        float* C = &pl->cost[(size_t)r * 7];
+        uint32_t cnt = b.count(r);
+        float c_int = A * PT_COST_NODE + D[8];
+        if (cnt <= max_leaf && A * ((float)cnt * PT_COST_TRI) <= c_int) { C[0] = A * ((float)cnt * PT_COST_TRI); P[7] = 1; }
+        else C[0] = c_int;
+        for (int i = 2; i <= 7; ++i) {
+            if (C[i - 2] <= D[i]) { C[i - 1] = C[i - 2]; P[i - 2] |= 0x80; } else C[i - 1] = D[i];
+        }
+    }
+}
+// children of the wide node that stands for internal BVH2 node `ref`, in left-to-right order
+static int plan_children(const Bvh2& b, const CollapsePlan& pl, uint32_t ref, uint32_t* C) {
+    struct It { uint32_t r; int j; };
+    It st[16]; int sp = 0, nc = 0;
+    int k = pl.plan[(size_t)ref * 8 + 6] & 15;
+    st[sp++] = {b.right[ref], 8 - k}; st[sp++] = {b.left[ref], k};
+    while (sp) {
+        It it = st[--sp];
+        if (it.r >= b.n - 1 || it.j == 1) { C[nc++] = it.r; continue; }
+        uint8_t p = pl.plan[(size_t)it.r * 8 + (it.j - 2)];
+        if (p & 0x80) { st[sp++] = {it.r, it.j - 1}; continue; }
+        int kk = p & 15;
+        st[sp++] = {b.right[it.r], it.j - kk}; st[sp++] = {b.left[it.r], kk};
+    }
+    return nc;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // BVH2 -> BVH8 collapse (breadth first).  leaf_seq receives, in leaf order, the sorted positions of the
 // primitives; node.tri_base + offset indexes into it.
 // ---------------------------------------------------------------------------------------------------
@@ -117,6 +181,10 @@ void collapse8(const Bvh2& b, uint32_t max_leaf, float pad, std::vector<PtNode8>
     uint32_t root_ref = (n == 1) ? 0u /* leaf 0 == ref n-1 == 0 */ : 0u;
     std::vector<uint32_t> level{root_ref}, next;
     uint32_t level_start = 0;
+    const bool use_plan = getenv("ORC_PLAN") != nullptr;   // experiment switch while the device build still collapses greedily
+    CollapsePlan plan;
+    if (use_plan) plan_collapse(b, max_leaf, &plan);
+    auto is_leaf_slot = [&](uint32_t r) { return n == 1 || r >= n - 1 || (use_plan ? plan.plan[(size_t)r * 8 + 7] != 0 : b.count(r) <= max_leaf); };
     while (!level.empty()) {
         next.clear();
         uint32_t next_start = level_start + (uint32_t)level.size();
@@ -126,6 +194,7 @@ void collapse8(const Bvh2& b, uint32_t max_leaf, float pad, std::vector<PtNode8>
             uint32_t C[8]; int nc = 0;
             bool ref_is_leaf = (n == 1) || b.count(ref) <= max_leaf;
             if (ref_is_leaf) C[nc++] = (n == 1) ? 0u : ref;
+            else if (use_plan) nc = plan_children(b, plan, ref, C);
             else {
                 C[nc++] = b.left[ref]; C[nc++] = b.right[ref];
                 while (nc < 8) {
@@ -185,7 +254,7 @@ void collapse8(const Bvh2& b, uint32_t max_leaf, float pad, std::vector<PtNode8>
                 nd.qloy[s] = (uint8_t)pt_quant_lo(cb.lo[1] - pad, p[1], inv[1]); nd.qhiy[s] = (uint8_t)pt_quant_hi(cb.hi[1] + pad, p[1], inv[1]);
                 nd.qloz[s] = (uint8_t)pt_quant_lo(cb.lo[2] - pad, p[2], inv[2]); nd.qhiz[s] = (uint8_t)pt_quant_hi(cb.hi[2] + pad, p[2], inv[2]);
                 uint32_t cnt = (n == 1) ? 1 : b.count(C[k]);
-                if (cnt <= max_leaf) {
+                if (is_leaf_slot(C[k])) {
                     uint32_t fp = (n == 1) ? 0 : b.lo_pos(C[k]);
                     nd.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | tri_off);
                     for (uint32_t q = 0; q < cnt; ++q) leaf_seq->push_back(fp + q);
@@ -354,7 +423,7 @@ struct Trav {
     const Scene* s; bool any; float tmin; Hit* best; Counters* c; bool done = false;
     RayC world;
 
-    // child-box test on the quantised grid: the same roundings as the device (fma(q, scale*idir, (p-o)*idir))
+    // child-box test on the quantised grid: the same roundings as the device (fma(QBIAS + q, scale*idir, (p-o)*idir - QBIAS*scale*idir))
     bool child_hit(const PtNode8& n, int slot, const RayC& r) const {
         const float p[3] = {n.px, n.py, n.pz};
         const uint8_t e[3] = {n.ex, n.ey, n.ez};
@@ -366,9 +435,10 @@ struct Trav {
         for (int k = 0; k < 3; ++k) {
             float a = pt_u2f((uint32_t)e[k] << 23) * id[k];
             float bb = (p[k] - o[k]) * id[k];
-            float err = pt_fma(pt_abs(a), 255.0f, pt_abs(bb)) * PT_SLAB_EPS;   // ray-dependent slack, same rule as the device (pt_layout.h)
-            float qn = (float)(r.neg[k] ? qh[k][slot] : ql[k][slot]), qf = (float)(r.neg[k] ? ql[k][slot] : qh[k][slot]);
-            tnk[k] = pt_fma(qn, a, bb - err); tfk[k] = pt_fma(qf, a, bb + err);
+            float err = pt_fma(pt_abs(a), PT_SLAB_QMAX, pt_abs(bb)) * PT_SLAB_EPS;   // ray-dependent slack, same rule as the device (pt_layout.h)
+            float cc = pt_fma(-PT_QBIAS, a, bb);                                     // the byte enters as QBIAS + q, the bias is folded in here
+            float qn = PT_QBIAS + (float)(r.neg[k] ? qh[k][slot] : ql[k][slot]), qf = PT_QBIAS + (float)(r.neg[k] ? ql[k][slot] : qh[k][slot]);
+            tnk[k] = pt_fma(qn, a, cc - err); tfk[k] = pt_fma(qf, a, cc + err);
         }
         tn = fmaxf(fmaxf(tnk[0], tnk[1]), fmaxf(tnk[2], tmin));
         tf = fminf(fminf(tfk[0], tfk[1]), fminf(tfk[2], best->t));
