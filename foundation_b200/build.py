@@ -31,7 +31,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the C-ABI library for sm_100a if it is missing or older than its sources.
     Safe under concurrent callers (one rank per GPU all importing at once): an exclusive file lock serialises the build and the
     result is moved into place atomically, so no process can ever dlopen a half-written library."""
-    if not force and not is_stale():
+    if not force and (os.environ.get("FOUNDATION_PT_LIB") or not is_stale()):   # an A/B variant is used as it is, never rebuilt from the tree
         return LIB_PATH
     import fcntl
     os.makedirs(LIB_DIR, exist_ok=True)

@@ -224,15 +224,16 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
     PT_CK(cudaEventRecord(ctx->ev3, ctx->stream));
     keys_b.release(); vals_b.release(); hist.release();
     // BVH2
-    DevBuf left, right, first, last, parent, box, flags;
+    DevBuf left, right, first, last, parent, box, flags, cost, plan;
     size_t ni = n > 1 ? n - 1 : 1;
+    PT_CK(cost.alloc(ni * 32)); PT_CK(plan.alloc(ni * 8));
     PT_CK(left.alloc(ni * 4)); PT_CK(right.alloc(ni * 4)); PT_CK(first.alloc(ni * 4)); PT_CK(last.alloc(ni * 4));
     PT_CK(parent.alloc((2 * (size_t)n) * 4)); PT_CK(box.alloc((2 * (size_t)n) * sizeof(PtBox))); PT_CK(flags.alloc(ni * 4));
     PT_CK(cudaMemsetAsync(flags.p, 0, ni * 4, ctx->stream));
     PtBvh2 b; b.n = n; b.left = left.as<uint32_t>(); b.right = right.as<uint32_t>(); b.first = first.as<uint32_t>(); b.last = last.as<uint32_t>();
-    b.parent = parent.as<uint32_t>(); b.box = box.as<PtBox>();
+    b.parent = parent.as<uint32_t>(); b.box = box.as<PtBox>(); b.cost = cost.as<float>(); b.plan = plan.as<uint64_t>();
     if (n > 1) PT_LAUNCH(ctx, k_karras, grid_for(ctx, n - 1, 256, 8), 256, keys.as<uint64_t>(), b);
-    PT_LAUNCH(ctx, k_refit, grid_for(ctx, n, 256, 8), 256, b, d_prim_box, vals.as<uint32_t>(), flags.as<uint32_t>());
+    PT_LAUNCH(ctx, k_refit, grid_for(ctx, n, 256, 8), 256, b, d_prim_box, vals.as<uint32_t>(), flags.as<uint32_t>(), max_leaf);
     // collapse, level by level
     DevBuf nodes_tmp, refs_a, refs_b, slots, n_int, n_prim, totals;
     PT_CK(nodes_tmp.alloc((size_t)n * sizeof(PtNode8)));

@@ -294,22 +294,48 @@ __device__ __forceinline__ PtBox pt_ldcg_box(const PtBox* p) {
     PtBox b; b.lox = __ldcg(f); b.loy = __ldcg(f + 1); b.loz = __ldcg(f + 2); b.hix = __ldcg(f + 3); b.hiy = __ldcg(f + 4); b.hiz = __ldcg(f + 5);
     return b;
 }
-__global__ void __launch_bounds__(256) k_refit(PtBvh2 b, const PtBox* prim_box, const uint32_t* order, uint32_t* flags) {
+// Also runs the collapse plan (pt_plan_node) on the way up: the thread that completes a node has its own subtree's seven costs in
+// registers and reads the sibling's back from L2, exactly like the boxes.
+__global__ void __launch_bounds__(256) k_refit(PtBvh2 b, const PtBox* prim_box, const uint32_t* order, uint32_t* flags, uint32_t max_leaf) {
     const uint32_t n = b.n;
     for (uint32_t j = pt_gtid(); j < n; j += pt_gsize()) {
         PtBox mine = prim_box[order[j]];          // the box of the subtree this thread is carrying upwards stays in registers
         uint32_t me = n - 1 + j;
         b.box[me] = mine;
         if (n == 1) return;
+        float mc[7];
+        {
+            const float lc = pt_plan_leaf_cost(mine);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) mc[i] = lc;
+        }
         for (;;) {
             uint32_t cur = b.parent[me];
-            __threadfence();                       // publish box[me] before announcing arrival
+            __threadfence();                       // publish box[me] and cost[me] before announcing arrival
             if (atomicAdd(&flags[cur], 1u) == 0u) break;   // first arriver leaves; the second one owns the parent
-            uint32_t l = b.left[cur];
-            PtBox s = pt_ldcg_box(&b.box[l == me ? b.right[cur] : l]);     // only the sibling has to be read back (L2, not L1)
+            const uint32_t l = b.left[cur];
+            const bool me_left = l == me;
+            const uint32_t sib = me_left ? b.right[cur] : l;
+            PtBox s = pt_ldcg_box(&b.box[sib]);     // only the sibling has to be read back (L2, not L1)
+            float sc[7];
+            if (sib >= n - 1) {
+                const float lc = pt_plan_leaf_cost(s);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) sc[i] = lc;
+            } else {
+                const float4 c0 = __ldcg(reinterpret_cast<const float4*>(b.cost + 8 * (size_t)sib)), c1 = __ldcg(reinterpret_cast<const float4*>(b.cost + 8 * (size_t)sib + 4));
+                sc[0] = c0.x; sc[1] = c0.y; sc[2] = c0.z; sc[3] = c0.w; sc[4] = c1.x; sc[5] = c1.y; sc[6] = c1.z;
+            }
             mine.lox = pt_min(mine.lox, s.lox); mine.loy = pt_min(mine.loy, s.loy); mine.loz = pt_min(mine.loz, s.loz);
             mine.hix = pt_max(mine.hix, s.hix); mine.hiy = pt_max(mine.hiy, s.hiy); mine.hiz = pt_max(mine.hiz, s.hiz);
             b.box[cur] = mine;
+            float cl[7], cr[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { cl[i] = me_left ? mc[i] : sc[i]; cr[i] = me_left ? sc[i] : mc[i]; }
+            const uint32_t cnt = b.last[cur] - b.first[cur] + 1u;
+            b.plan[cur] = pt_plan_node(cl, cr, pt_box_area(mine.lox, mine.loy, mine.loz, mine.hix, mine.hiy, mine.hiz), cnt, max_leaf, mc);
+            float4* dst = reinterpret_cast<float4*>(b.cost + 8 * (size_t)cur);
+            dst[0] = make_float4(mc[0], mc[1], mc[2], mc[3]); dst[1] = make_float4(mc[4], mc[5], mc[6], 0.0f);
             if (cur == 0) break;
             me = cur;
         }

@@ -232,8 +232,8 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
         } else {
             // TLAS leaf: enter the instance.  Save the remaining groups, push the return sentinel.
             if (s->sp + 3 > PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
+            if (s->ng.y & 0xff000000u) stack[s->sp++] = s->ng;   // popped last: the node's remaining instances come before its internal children
             if (s->tg.y) stack[s->sp++] = s->tg;
-            if (s->ng.y & 0xff000000u) stack[s->sp++] = s->ng;
             PtU2 sentinel; sentinel.x = PT_NONE; sentinel.y = 0; stack[s->sp++] = sentinel;
             const PtU4* ip = sc.instances + 7 * (size_t)(s->tg.x + k);
             PtU4 m0 = pt_load4(ip), m1 = pt_load4(ip + 1), m2 = pt_load4(ip + 2), m6 = pt_load4(ip + 6);

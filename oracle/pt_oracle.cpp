@@ -20,7 +20,7 @@
 //   - std::stable_sort on (key, index)         (product: hand-written LSD radix sort)
 //   - recursive BVH8 traversal                 (product: stack of node/triangle groups)
 //   - one scalar loop per path                 (product: wavefront queues, compaction, material sort)
-//   - sequential BFS collapse                  (product: level-synchronous kernels + scans)
+//   - sequential BFS collapse, plan by post-order (product: level-synchronous kernels + scans, plan inside the refit)
 // Conventions restated from the reference: column-major view/proj (Renderer.cpp:28-33), Z-up RH camera and
 // Vulkan Y flip (Renderer.cpp:373-380), top-left pixel origin, 1920x1080 RGBA8 target (Renderer.cpp:40-41).
 #include <algorithm>
@@ -110,7 +110,7 @@ void build_lbvh(const std::vector<Box3>& pbox, const std::vector<pt_v3>& cent, c
 // Collapse plan: the surface-area-cost dynamic programme of Ylitie, Karras, Laine (HPG 2017, section 3.1).
 // cost[ref][i-1], i = 1..7 = cheapest way to represent the subtree of BVH2 node `ref` as at most i children
 // of a wide node; plan[ref][j-2], j = 2..8 = how many of j slots go to the left child (low nibble), bit 7 =
-// "j-1 slots are as cheap"; plan[ref][7] = 1 when the subtree is one leaf slot.
+// "j-1 slots are as cheap"; plan[ref][7] is unused.
 // ---------------------------------------------------------------------------------------------------
 struct CollapsePlan { std::vector<float> cost; std::vector<uint8_t> plan; };
 
@@ -145,9 +145,7 @@ void plan_collapse(const Bvh2& b, uint32_t max_leaf, CollapsePlan* pl) {
         float A = ref_area(b, r);
         float* C = &pl->cost[(size_t)r * 7];
         uint32_t cnt = b.count(r);
-        float c_int = A * PT_COST_NODE + D[8];
-        if (cnt <= max_leaf && A * ((float)cnt * PT_COST_TRI) <= c_int) { C[0] = A * ((float)cnt * PT_COST_TRI); P[7] = 1; }
-        else C[0] = c_int;
+        C[0] = cnt <= max_leaf ? A * ((float)cnt * PT_COST_TRI) : A * PT_COST_NODE + D[8];   // a subtree that fits one leaf slot is always a leaf
         for (int i = 2; i <= 7; ++i) {
             if (C[i - 2] <= D[i]) { C[i - 1] = C[i - 2]; P[i - 2] |= 0x80; } else C[i - 1] = D[i];
         }
@@ -181,10 +179,8 @@ void collapse8(const Bvh2& b, uint32_t max_leaf, float pad, std::vector<PtNode8>
     uint32_t root_ref = (n == 1) ? 0u /* leaf 0 == ref n-1 == 0 */ : 0u;
     std::vector<uint32_t> level{root_ref}, next;
     uint32_t level_start = 0;
-    const bool use_plan = getenv("ORC_PLAN") != nullptr;   // experiment switch while the device build still collapses greedily
     CollapsePlan plan;
-    if (use_plan) plan_collapse(b, max_leaf, &plan);
-    auto is_leaf_slot = [&](uint32_t r) { return n == 1 || r >= n - 1 || (use_plan ? plan.plan[(size_t)r * 8 + 7] != 0 : b.count(r) <= max_leaf); };
+    plan_collapse(b, max_leaf, &plan);
     while (!level.empty()) {
         next.clear();
         uint32_t next_start = level_start + (uint32_t)level.size();
@@ -194,22 +190,7 @@ void collapse8(const Bvh2& b, uint32_t max_leaf, float pad, std::vector<PtNode8>
             uint32_t C[8]; int nc = 0;
             bool ref_is_leaf = (n == 1) || b.count(ref) <= max_leaf;
             if (ref_is_leaf) C[nc++] = (n == 1) ? 0u : ref;
-            else if (use_plan) nc = plan_children(b, plan, ref, C);
-            else {
-                C[nc++] = b.left[ref]; C[nc++] = b.right[ref];
-                while (nc < 8) {
-                    int best = -1; float best_area = -INFINITY;
-                    for (int k = 0; k < nc; ++k) {
-                        if (b.count(C[k]) <= max_leaf) continue;
-                        const Box3& x = b.box[C[k]];
-                        float ar = pt_box_area(x.lo[0], x.lo[1], x.lo[2], x.hi[0], x.hi[1], x.hi[2]);
-                        if (ar > best_area) { best_area = ar; best = k; }
-                    }
-                    if (best < 0) break;
-                    uint32_t r = C[best];
-                    C[best] = b.left[r]; C[nc++] = b.right[r];
-                }
-            }
+            else nc = plan_children(b, plan, ref, C);
             const Box3& nb = b.box[(n == 1) ? 0 : ref];
             // greedy octant slot assignment
             float cost[8][8];
@@ -254,7 +235,7 @@ void collapse8(const Bvh2& b, uint32_t max_leaf, float pad, std::vector<PtNode8>
                 nd.qloy[s] = (uint8_t)pt_quant_lo(cb.lo[1] - pad, p[1], inv[1]); nd.qhiy[s] = (uint8_t)pt_quant_hi(cb.hi[1] + pad, p[1], inv[1]);
                 nd.qloz[s] = (uint8_t)pt_quant_lo(cb.lo[2] - pad, p[2], inv[2]); nd.qhiz[s] = (uint8_t)pt_quant_hi(cb.hi[2] + pad, p[2], inv[2]);
                 uint32_t cnt = (n == 1) ? 1 : b.count(C[k]);
-                if (is_leaf_slot(C[k])) {
+                if (cnt <= max_leaf) {
                     uint32_t fp = (n == 1) ? 0 : b.lo_pos(C[k]);
                     nd.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | tri_off);
                     for (uint32_t q = 0; q < cnt; ++q) leaf_seq->push_back(fp + q);

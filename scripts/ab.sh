@@ -4,6 +4,6 @@ args="$1"; shift
 for rep in 1 2; do
   for lib in "$@"; do
     echo "== $lib (pass $rep)"
-    FOUNDATION_PT_LIB=$lib timeout 600 python scripts/probe.py $args 2>&1 | grep -E "closest|any-hit|render"
+    FOUNDATION_PT_LIB=$lib timeout 600 python scripts/probe.py $args 2>&1 | grep -E "commit|closest|any:|render"
   done
 done

@@ -27,7 +27,9 @@ uint32_t emu_build(const float* pbox, const float* cent, uint32_t n, uint32_t ma
     for (uint32_t i = 0; i < n; ++i) { keys[i] = kv[i].first; order_out[i] = kv[i].second; }
     std::vector<uint32_t> left(n), right(n), first(n), last(n), parent(2 * (size_t)n), flags(n, 0);
     std::vector<PtBox> box(2 * (size_t)n);
-    PtBvh2 b{n, left.data(), right.data(), first.data(), last.data(), parent.data(), box.data()};
+    std::vector<float> cost(8 * (size_t)n, 0.0f);
+    std::vector<uint64_t> plan(n, 0);
+    PtBvh2 b{n, left.data(), right.data(), first.data(), last.data(), parent.data(), box.data(), cost.data(), plan.data()};
     for (uint32_t i = 0; i + 1 < n; ++i) pt_karras_node(i, keys.data(), b);
     // refit: sequential emulation of the second-arriver rule
     for (uint32_t j = 0; j < n; ++j) {
@@ -39,6 +41,13 @@ uint32_t emu_build(const float* pbox, const float* cent, uint32_t n, uint32_t ma
             if (flags[cur]++ == 0) break;
             PtBox l = box[left[cur]], r = box[right[cur]];
             box[cur] = PtBox{pt_min(l.lox, r.lox), pt_min(l.loy, r.loy), pt_min(l.loz, r.loz), pt_max(l.hix, r.hix), pt_max(l.hiy, r.hiy), pt_max(l.hiz, r.hiz)};
+            float cl[7], cr[7];
+            for (int i = 0; i < 7; ++i) {
+                cl[i] = left[cur] >= n - 1 ? pt_plan_leaf_cost(l) : cost[8 * (size_t)left[cur] + i];
+                cr[i] = right[cur] >= n - 1 ? pt_plan_leaf_cost(r) : cost[8 * (size_t)right[cur] + i];
+            }
+            const PtBox u = box[cur];
+            plan[cur] = pt_plan_node(cl, cr, pt_box_area(u.lox, u.loy, u.loz, u.hix, u.hiy, u.hiz), last[cur] - first[cur] + 1u, max_leaf, &cost[8 * (size_t)cur]);
             if (cur == 0) break;
             cur = parent[cur];
         }
