@@ -233,7 +233,13 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
     PtBvh2 b; b.n = n; b.left = left.as<uint32_t>(); b.right = right.as<uint32_t>(); b.first = first.as<uint32_t>(); b.last = last.as<uint32_t>();
     b.parent = parent.as<uint32_t>(); b.box = box.as<PtBox>(); b.cost = cost.as<float>(); b.plan = plan.as<uint64_t>();
     if (n > 1) PT_LAUNCH(ctx, k_karras, grid_for(ctx, n - 1, 256, 8), 256, keys.as<uint64_t>(), b);
-    PT_LAUNCH(ctx, k_refit, grid_for(ctx, n, 256, 8), 256, b, d_prim_box, vals.as<uint32_t>(), flags.as<uint32_t>(), max_leaf);
+    {   // A4: tile-local part (shared memory, round-synchronous), then the few subtree roots per tile climb the upper levels
+        DevBuf up_list, up_count;   // freed stream-ordered when the scope ends
+        PT_CK(up_list.alloc((size_t)n * 4)); PT_CK(up_count.alloc(16));
+        PT_CK(cudaMemsetAsync(up_count.p, 0, 4, ctx->stream));
+        PT_LAUNCH(ctx, k_refit, grid_for(ctx, n, PT_REFIT_TILE, 8), PT_REFIT_TILE, b, d_prim_box, vals.as<uint32_t>(), up_list.as<uint32_t>(), up_count.as<uint32_t>(), max_leaf);
+        if (n > 1) PT_LAUNCH(ctx, k_refit_up, grid_for(ctx, n / 16 + 1, 128, 8), 128, b, up_list.as<uint32_t>(), up_count.as<uint32_t>(), flags.as<uint32_t>(), max_leaf);
+    }
     // collapse, level by level
     DevBuf nodes_tmp, refs_a, refs_b, slots, n_int, n_prim, totals;
     PT_CK(nodes_tmp.alloc((size_t)n * sizeof(PtNode8)));

@@ -294,99 +294,168 @@ __device__ __forceinline__ PtBox pt_ldcg_box(const PtBox* p) {
     PtBox b; b.lox = __ldcg(f); b.loy = __ldcg(f + 1); b.loz = __ldcg(f + 2); b.hix = __ldcg(f + 3); b.hiy = __ldcg(f + 4); b.hiz = __ldcg(f + 5);
     return b;
 }
-// Also runs the collapse plan (pt_plan_node) on the way up: the thread that completes a node has its own subtree's seven costs in
-// registers and reads the sibling's back, exactly like the boxes.
-// Tiled: a block owns PT_REFIT_TILE consecutive sorted leaves.  A node whose leaf range [first, last] lies inside the tile has both
-// subtrees finished by threads of this block, so its arrival flag, the sibling's box and the sibling's costs live in SHARED memory:
-// no global atomic, no device-wide fence, no L2 round trip for the bottom log2(TILE) levels, which hold all but 1/TILE of the nodes
-// (the first version paid a __threadfence + a global atomic + two dependent L2 reads per node and ran at 4.5 % of the HBM bound).
-// Nodes that straddle tiles use the global protocol as before; every node's box / costs / plan are still written to global memory
-// because the collapse reads them.
+// A4 also runs the collapse plan (pt_plan_node) for every internal node: a node needs the boxes and the seven costs of both children.
+//
+// Tiled and round-synchronous.  A block owns PT_REFIT_TILE consecutive sorted leaves.  A node whose leaf range [first, last] lies
+// inside the tile ("local": all but ~1/TILE of the nodes) has both subtrees inside the tile, so everything about it lives in SHARED
+// memory: topology (loaded once per tile, coalesced), arrival counter, boxes, costs.  Local nodes are processed in rounds: whoever
+// delivers the second child of a node appends the node to the next round's queue, and the next round hands the queued nodes to
+// consecutive threads.  The dynamic programme (~300 instructions per node) therefore runs with full warps; in the classic "second
+// arriver climbs on" formulation it runs with 1-4 live lanes per warp, which is what made the first version issue-bound at 3.4 ms
+// for 10 M triangles (5.8 % of DRAM peak).  Results of the tile are written back coalesced at the end.
+// The roots of the tile's maximal local subtrees are appended to a global list; k_refit_up continues from them with the global
+// protocol (device fence, global arrival counter, sibling read back from L2): a few threads per tile, log-many levels.
 #define PT_REFIT_TILE 256
-__device__ __forceinline__ PtBox pt_lds_box(const PtBox* p) {   // volatile: written by another thread of the block, ordered by the arrival flag
+__device__ __forceinline__ PtBox pt_lds_box(const PtBox* p) {   // volatile: written by another thread of the block in an earlier round
     const volatile float* f = reinterpret_cast<const volatile float*>(p);
     PtBox b; b.lox = f[0]; b.loy = f[1]; b.loz = f[2]; b.hix = f[3]; b.hiy = f[4]; b.hiz = f[5];
     return b;
 }
-__global__ void __launch_bounds__(PT_REFIT_TILE) k_refit(PtBvh2 b, const PtBox* prim_box, const uint32_t* order, uint32_t* flags, uint32_t max_leaf) {
-    __shared__ PtBox s_box[2 * PT_REFIT_TILE];          // [0, TILE): internal node tile_lo + i;  [TILE, 2 TILE): leaf tile_lo + i
-    __shared__ float s_cost[PT_REFIT_TILE][7];
-    __shared__ uint32_t s_flag[PT_REFIT_TILE];
+__device__ __forceinline__ void pt_box_union(PtBox& a, const PtBox& s) {
+    a.lox = pt_min(a.lox, s.lox); a.loy = pt_min(a.loy, s.loy); a.loz = pt_min(a.loz, s.loz);
+    a.hix = pt_max(a.hix, s.hix); a.hiy = pt_max(a.hiy, s.hiy); a.hiz = pt_max(a.hiz, s.hiz);
+}
+__global__ void __launch_bounds__(PT_REFIT_TILE) k_refit(PtBvh2 b, const PtBox* prim_box, const uint32_t* order, uint32_t* up_list, uint32_t* up_count, uint32_t max_leaf) {
+    constexpr uint32_t T = PT_REFIT_TILE;
+    __shared__ PtBox s_box[2 * T];                       // [0, T): internal node tile_lo + i;  [T, 2T): leaf tile_lo + i
+    __shared__ float4 s_cost[T][2];                      // cost(node, 1..7) of internal node tile_lo + i
+    __shared__ unsigned long long s_plan[T];
+    __shared__ uint32_t s_left[T], s_right[T], s_first[T], s_last[T], s_par[2 * T];   // s_par: [0, T) internal, [T, 2T) leaves
+    __shared__ uint32_t s_flag[T];                       // children delivered (2 = node processed in this tile)
+    __shared__ uint32_t s_q[3][T / 2];                   // round queues (read / fill / being reset): a round never holds more than T / 2 nodes
+    __shared__ uint32_t s_up[T];                         // roots of the maximal local subtrees (refs), to be continued globally
+    __shared__ uint32_t s_qn[3], s_upn;
     const uint32_t n = b.n, tid = threadIdx.x;
     if (n == 1) { if (pt_gtid() == 0) b.box[0] = prim_box[order[0]]; return; }
-    for (uint32_t tile_lo = blockIdx.x * PT_REFIT_TILE; tile_lo < n; tile_lo += gridDim.x * PT_REFIT_TILE) {
-        const uint32_t tile_hi = min(n, tile_lo + PT_REFIT_TILE) - 1u;   // last leaf position of the tile
-        s_flag[tid] = 0;
-        __syncthreads();
+    for (uint32_t tile_lo = blockIdx.x * T; tile_lo < n; tile_lo += gridDim.x * T) {
+        const uint32_t tile_hi = min(n, tile_lo + T) - 1u;   // last leaf position of the tile
         const uint32_t j = tile_lo + tid;
+        // ---- load the tile: leaf boxes (gather), topology of the internal nodes tile_lo .. tile_hi
         if (j < n) {
-            PtBox mine = prim_box[order[j]];          // the box of the subtree this thread is carrying upwards stays in registers
-            uint32_t me = n - 1 + j;
-            b.box[me] = mine;
-            s_box[PT_REFIT_TILE + tid] = mine;
-            float mc[7];
-            {
-                const float lc = pt_plan_leaf_cost(mine);
-#pragma unroll
-                for (int i = 0; i < 7; ++i) mc[i] = lc;
-            }
-            for (;;) {
-                const uint32_t cur = b.parent[me];
-                const uint32_t f = b.first[cur], l = b.last[cur];
-                const bool local = f >= tile_lo && l <= tile_hi;
-                PtBox s;
-                float sc[7];
-                uint32_t sib; bool me_left;
-                if (local) {
-                    __threadfence_block();                 // publish s_box / s_cost of `me` to the block before announcing arrival
-                    if (atomicAdd(&s_flag[cur - tile_lo], 1u) == 0u) break;   // first arriver leaves; the second one owns the parent
-                    __threadfence_block();
-                    const uint32_t lft = b.left[cur];
-                    me_left = lft == me;
-                    sib = me_left ? b.right[cur] : lft;
-                    if (sib >= n - 1) {
-                        s = pt_lds_box(&s_box[PT_REFIT_TILE + (sib - (n - 1)) - tile_lo]);
-                    } else {
-                        s = pt_lds_box(&s_box[sib - tile_lo]);
-#pragma unroll
-                        for (int i = 0; i < 7; ++i) sc[i] = *const_cast<volatile float*>(&s_cost[sib - tile_lo][i]);
-                    }
-                } else {
-                    __threadfence();                       // publish box[me] and cost[me] device-wide before announcing arrival
-                    if (atomicAdd(&flags[cur], 1u) == 0u) break;
-                    const uint32_t lft = b.left[cur];
-                    me_left = lft == me;
-                    sib = me_left ? b.right[cur] : lft;
-                    s = pt_ldcg_box(&b.box[sib]);           // the sibling may come from another block: read it back from L2, not L1
-                    if (sib < n - 1) {
-                        const float4 c0 = __ldcg(reinterpret_cast<const float4*>(b.cost + 8 * (size_t)sib)), c1 = __ldcg(reinterpret_cast<const float4*>(b.cost + 8 * (size_t)sib + 4));
-                        sc[0] = c0.x; sc[1] = c0.y; sc[2] = c0.z; sc[3] = c0.w; sc[4] = c1.x; sc[5] = c1.y; sc[6] = c1.z;
-                    }
-                }
-                if (sib >= n - 1) {
-                    const float lc = pt_plan_leaf_cost(s);
-#pragma unroll
-                    for (int i = 0; i < 7; ++i) sc[i] = lc;
-                }
-                mine.lox = pt_min(mine.lox, s.lox); mine.loy = pt_min(mine.loy, s.loy); mine.loz = pt_min(mine.loz, s.loz);
-                mine.hix = pt_max(mine.hix, s.hix); mine.hiy = pt_max(mine.hiy, s.hiy); mine.hiz = pt_max(mine.hiz, s.hiz);
-                b.box[cur] = mine;
-                float cl[7], cr[7];
-#pragma unroll
-                for (int i = 0; i < 7; ++i) { cl[i] = me_left ? mc[i] : sc[i]; cr[i] = me_left ? sc[i] : mc[i]; }
-                b.plan[cur] = pt_plan_node(cl, cr, pt_box_area(mine.lox, mine.loy, mine.loz, mine.hix, mine.hiy, mine.hiz), l - f + 1u, max_leaf, mc);
-                float4* dst = reinterpret_cast<float4*>(b.cost + 8 * (size_t)cur);
-                dst[0] = make_float4(mc[0], mc[1], mc[2], mc[3]); dst[1] = make_float4(mc[4], mc[5], mc[6], 0.0f);
-                if (local) {
-                    s_box[cur - tile_lo] = mine;
-#pragma unroll
-                    for (int i = 0; i < 7; ++i) s_cost[cur - tile_lo][i] = mc[i];
-                }
-                if (cur == 0) break;
-                me = cur;
-            }
+            const PtBox lb = prim_box[order[j]];
+            s_box[T + tid] = lb;
+            b.box[n - 1 + j] = lb;
+            s_par[T + tid] = b.parent[n - 1 + j];
         }
+        if (j < n - 1) {
+            s_left[tid] = b.left[j]; s_right[tid] = b.right[j]; s_first[tid] = b.first[j]; s_last[tid] = b.last[j];
+            s_par[tid] = j ? b.parent[j] : 0u;
+        }
+        s_flag[tid] = 0;
+        if (tid == 0) { s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0; s_upn = 0; }
+        __syncthreads();
+        // child `ref` is finished: deliver it to its parent p.  Second delivery queues p for the next round; a parent that is not local
+        // ends the tile's part of this subtree.
+        auto deliver = [&](uint32_t ref, uint32_t p, uint32_t q) {
+            const uint32_t lp = p - tile_lo;     // a node's index is an end point of its leaf range, so a local node has tile_lo <= p <= tile_hi
+            const bool local = p >= tile_lo && p <= tile_hi && s_first[lp] >= tile_lo && s_last[lp] <= tile_hi;
+            if (!local) { s_up[atomicAdd(&s_upn, 1u)] = ref; return; }
+            if (atomicAdd(&s_flag[lp], 1u) == 1u) s_q[q][atomicAdd(&s_qn[q], 1u)] = p;
+        };
+        if (j < n) deliver(n - 1 + j, s_par[T + tid], 0u);
+        __syncthreads();
+        // ---- rounds over the local nodes
+        for (uint32_t cur = 0;; cur = cur == 2u ? 0u : cur + 1u) {
+            const uint32_t cnt = s_qn[cur], nxt = cur == 2u ? 0u : cur + 1u;
+            if (cnt == 0) break;                          // block-uniform: read after a barrier, not written before the next one
+            if (tid == 0) s_qn[nxt == 2u ? 0u : nxt + 1u] = 0;   // the queue after next: read in the previous round, filled in the next one
+            if (tid < cnt) {
+                const uint32_t p = s_q[cur][tid], lp = p - tile_lo;
+                const uint32_t L = s_left[lp], R = s_right[lp];
+                float cl[7], cr[7], mc[7];
+                PtBox bl, br;
+                if (L >= n - 1) {
+                    bl = pt_lds_box(&s_box[T + (L - (n - 1)) - tile_lo]);
+                    const float lc = pt_plan_leaf_cost(bl);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) cl[i] = lc;
+                } else {
+                    bl = pt_lds_box(&s_box[L - tile_lo]);
+                    const volatile float* c = reinterpret_cast<const volatile float*>(&s_cost[L - tile_lo][0]);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) cl[i] = c[i];
+                }
+                if (R >= n - 1) {
+                    br = pt_lds_box(&s_box[T + (R - (n - 1)) - tile_lo]);
+                    const float lc = pt_plan_leaf_cost(br);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) cr[i] = lc;
+                } else {
+                    br = pt_lds_box(&s_box[R - tile_lo]);
+                    const volatile float* c = reinterpret_cast<const volatile float*>(&s_cost[R - tile_lo][0]);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) cr[i] = c[i];
+                }
+                pt_box_union(bl, br);
+                s_box[lp] = bl;
+                s_plan[lp] = pt_plan_node(cl, cr, pt_box_area(bl.lox, bl.loy, bl.loz, bl.hix, bl.hiy, bl.hiz), s_last[lp] - s_first[lp] + 1u, max_leaf, mc);
+                s_cost[lp][0] = make_float4(mc[0], mc[1], mc[2], mc[3]); s_cost[lp][1] = make_float4(mc[4], mc[5], mc[6], 0.0f);
+                if (p != 0) deliver(p, s_par[lp], nxt);
+            }
+            __syncthreads();
+        }
+        // ---- write the tile's finished nodes back (coalesced), make them visible device-wide
+        if (j < n - 1 && s_flag[tid] == 2u) {
+            b.box[j] = s_box[tid];
+            float4* dst = reinterpret_cast<float4*>(b.cost + 8 * (size_t)j);
+            dst[0] = s_cost[tid][0]; dst[1] = s_cost[tid][1];
+            b.plan[j] = s_plan[tid];
+        }
+        // ---- the roots of the tile's maximal local subtrees are handed to k_refit_up (one global list, one atomic per tile).  Climbing
+        // on right here made the whole block wait at the tile's last barrier for a handful of fence + atomic + L2 round-trip chains:
+        // 73 % of all stall samples, 3.4 ms for 10 M triangles.
+        __syncthreads();
+        if (tid == 0) s_qn[0] = atomicAdd(up_count, s_upn);
+        __syncthreads();
+        if (tid < s_upn) up_list[s_qn[0] + tid] = s_up[tid];
         __syncthreads();                                   // the tile's shared state is reused by the block's next tile
+    }
+}
+// Upper part of the refit: every root of a tile-local subtree climbs with the classic protocol (publish, device fence, global arrival
+// counter; the second arriver reads the sibling back from L2 and owns the parent).  ~4 roots per tile, log-many levels.
+__global__ void __launch_bounds__(128) k_refit_up(PtBvh2 b, const uint32_t* up_list, const uint32_t* up_count, uint32_t* flags, uint32_t max_leaf) {
+    const uint32_t n = b.n, m = *up_count;
+    for (uint32_t k = pt_gtid(); k < m; k += pt_gsize()) {
+        uint32_t me = up_list[k];
+        PtBox mine = b.box[me];
+        float mc[7];
+        if (me >= n - 1) {
+            const float lc = pt_plan_leaf_cost(mine);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) mc[i] = lc;
+        } else {
+            const float4 c0 = *reinterpret_cast<const float4*>(b.cost + 8 * (size_t)me), c1 = *reinterpret_cast<const float4*>(b.cost + 8 * (size_t)me + 4);
+            mc[0] = c0.x; mc[1] = c0.y; mc[2] = c0.z; mc[3] = c0.w; mc[4] = c1.x; mc[5] = c1.y; mc[6] = c1.z;
+        }
+        for (;;) {
+            const uint32_t cur = b.parent[me];
+            __threadfence();                       // publish box[me] and cost[me] device-wide before announcing arrival
+            if (atomicAdd(&flags[cur], 1u) == 0u) break;   // first arriver leaves; the second one owns the parent
+            const uint32_t l = b.left[cur];
+            const bool me_left = l == me;
+            const uint32_t sib = me_left ? b.right[cur] : l;
+            const PtBox s = pt_ldcg_box(&b.box[sib]);       // written by another thread of this kernel (or by k_refit): read it from L2, not L1
+            float sc[7];
+            if (sib >= n - 1) {
+                const float lc = pt_plan_leaf_cost(s);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) sc[i] = lc;
+            } else {
+                const float4 c0 = __ldcg(reinterpret_cast<const float4*>(b.cost + 8 * (size_t)sib)), c1 = __ldcg(reinterpret_cast<const float4*>(b.cost + 8 * (size_t)sib + 4));
+                sc[0] = c0.x; sc[1] = c0.y; sc[2] = c0.z; sc[3] = c0.w; sc[4] = c1.x; sc[5] = c1.y; sc[6] = c1.z;
+            }
+            pt_box_union(mine, s);
+            b.box[cur] = mine;
+            float cl[7], cr[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { cl[i] = me_left ? mc[i] : sc[i]; cr[i] = me_left ? sc[i] : mc[i]; }
+            const uint32_t cnt = b.last[cur] - b.first[cur] + 1u;
+            b.plan[cur] = pt_plan_node(cl, cr, pt_box_area(mine.lox, mine.loy, mine.loz, mine.hix, mine.hiy, mine.hiz), cnt, max_leaf, mc);
+            float4* dst = reinterpret_cast<float4*>(b.cost + 8 * (size_t)cur);
+            dst[0] = make_float4(mc[0], mc[1], mc[2], mc[3]); dst[1] = make_float4(mc[4], mc[5], mc[6], 0.0f);
+            if (cur == 0) break;
+            me = cur;
+        }
     }
 }
 
