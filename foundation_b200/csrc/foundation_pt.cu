@@ -407,7 +407,7 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
     PtShadeScene ss;
     ss.sv = ctx->view; ss.mats = ctx->d_mats.as<PtMaterial>(); ss.num_mats = (uint32_t)ctx->mats.size();
     ss.sc.lights = ctx->d_lights.as<PtLight>(); ss.sc.num_lights = ctx->num_lights; ss.sc.light_area = ctx->light_area; ss.sc.ray_eps = ctx->ray_eps;
-    ss.sc.flags = ctx->cfg.flags; ss.sc.max_bounces = max_bounces;
+    ss.sc.flags = ctx->cfg.flags; ss.sc.seed = ctx->cfg.seed; ss.sc.max_bounces = max_bounces;
     ss.sc.bg[0] = ctx->cfg.background[0]; ss.sc.bg[1] = ctx->cfg.background[1]; ss.sc.bg[2] = ctx->cfg.background[2];
     const bool sort = (ctx->cfg.flags & FOUNDATION_PT_FLAG_MATERIAL_SORT) && !(ctx->cfg.flags & FOUNDATION_PT_FLAG_NO_MATERIAL_SORT);
     uint32_t* status = ctx->d_status.as<uint32_t>();

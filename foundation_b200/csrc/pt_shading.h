@@ -15,6 +15,7 @@
 #define PT_FLAG_NO_BSDF_EMISSION 4u
 #define PT_FLAG_MATERIAL_SORT 8u
 #define PT_FLAG_SOBOL_JITTER 16u
+#define PT_FLAG_SOBOL_PATH 32u
 
 struct PtShadeConsts {
     const PtLight* lights;
@@ -24,6 +25,7 @@ struct PtShadeConsts {
     uint32_t flags;
     uint32_t max_bounces;
     float bg[3];
+    uint64_t seed;         // the render seed (per-pixel scramble keys of PT_FLAG_SOBOL_PATH)
 };
 
 // Everything a path carries between bounces (SoA on the device, a local struct in the oracle).
@@ -77,6 +79,30 @@ PT_HD uint32_t pt_sobol2(uint32_t i) {
 PT_HD void pt_sobol02(uint32_t sample, uint32_t key0, uint32_t key1, float* x, float* y) {
     *x = (float)((pt_reverse_bits32(sample) ^ key0) >> 8) * 5.9604644775390625e-08f;
     *y = (float)((pt_sobol2(sample) ^ key1) >> 8) * 5.9604644775390625e-08f;
+}
+
+// Path dimensions (PT_FLAG_SOBOL_PATH): the two 2-D decisions of every path vertex — the point on the light (u1, u2) and the BSDF
+// direction (u4, u5) — take sample i of a (0,2)-sequence that is "padded" per (pixel, bounce, decision): the sample index is shuffled
+// and both coordinates are Owen-scrambled with the hash-based nested uniform scramble of Laine & Karras ("Stratified sampling for
+// stochastic transparency", 2011) as used by Burley, "Practical Hash-based Owen Scrambling" (JCGT 2020).  x ^= x * even only moves
+// information from low to high bits, so reverse -> hash -> reverse is a nested (Owen) permutation: every 2^k-sample prefix of every
+// decision stays a (0,2)-net, and different decisions are decorrelated by their keys.  Integer-only: bit-identical on both machines.
+// The 1-D decisions (light pick, lobe pick, Russian roulette) stay on the PCG32 stream, whose layout does not depend on the flag.
+PT_HD uint32_t pt_lk_hash(uint32_t x, uint32_t seed) {
+    x += seed;
+    x ^= x * 0x6c50b47cu; x ^= x * 0xb82f1e52u; x ^= x * 0xc7afe638u; x ^= x * 0x8d22f6e6u;
+    return x;
+}
+PT_HD uint32_t pt_owen32(uint32_t x, uint32_t seed) { return pt_reverse_bits32(pt_lk_hash(pt_reverse_bits32(x), seed)); }
+PT_HD void pt_sobol02_padded(uint32_t sample, uint64_t key, float* x, float* y) {
+    const uint64_t k2 = pt_mix64(key);
+    const uint32_t i = pt_owen32(sample, (uint32_t)key);                         // shuffled index (nested: aligned 2^k blocks stay blocks)
+    *x = (float)(pt_owen32(pt_reverse_bits32(i), (uint32_t)(key >> 32)) >> 8) * 5.9604644775390625e-08f;
+    *y = (float)(pt_owen32(pt_sobol2(i), (uint32_t)k2) >> 8) * 5.9604644775390625e-08f;
+}
+// key of decision `which` (0 = light point, 1 = BSDF direction) at path vertex `bounce` of `pixel`
+PT_HD uint64_t pt_path_dim_key(uint64_t seed, uint32_t pixel, uint32_t bounce, uint32_t which) {
+    return pt_mix64(seed ^ pt_mix64(0x50b02ull + pixel + ((uint64_t)(2u * bounce + which + 1u) << 32)));
 }
 
 PT_HD void pt_path_init(PtPath* p, const PtCamera& cam, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t width, uint32_t height,
@@ -215,6 +241,8 @@ PT_HD bool pt_shade_vertex(PtPath* path, const PtShadeConsts& sc, float t, pt_v3
 
     // B4: next-event estimation (always consumes 3 numbers so the stream layout is fixed)
     float u0 = pt_rng_f(&path->rng), u1 = pt_rng_f(&path->rng), u2 = pt_rng_f(&path->rng);
+    const uint32_t sample = (uint32_t)(path->rng.inc >> 33);   // the stream id is (sample << 32 | pixel) << 1 | 1 (pt_rng_for)
+    if (sc.flags & PT_FLAG_SOBOL_PATH) pt_sobol02_padded(sample, pt_path_dim_key(sc.seed, path->pixel, path->bounce, 0u), &u1, &u2);
     if (!(sc.flags & PT_FLAG_NO_NEE) && sc.num_lights > 0) {
         PtLight lt = sc.lights[pt_pick_light(sc.lights, sc.num_lights, u0)];
         float su = pt_sqrt(u1);
@@ -243,6 +271,7 @@ PT_HD bool pt_shade_vertex(PtPath* path, const PtShadeConsts& sc, float t, pt_v3
 
     // B3: BSDF sample
     float u3 = pt_rng_f(&path->rng), u4 = pt_rng_f(&path->rng), u5 = pt_rng_f(&path->rng), u6 = pt_rng_f(&path->rng);
+    if (sc.flags & PT_FLAG_SOBOL_PATH) pt_sobol02_padded(sample, pt_path_dim_key(sc.seed, path->pixel, path->bounce, 1u), &u4, &u5);
     pt_v3 wi;
     if (!pt_bsdf_sample(bsdf, wo, u3, u4, u5, &wi)) return false;
     pt_v3 f; float pdf;

@@ -17,7 +17,7 @@ from . import build as _build
 from .scenes import HIT_DTYPE, RAY_DTYPE, Scene  # noqa: F401
 
 OK, ERR_ARGUMENT, ERR_STATE, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-FLAG_NO_MATERIAL_SORT, FLAG_NO_NEE, FLAG_NO_BSDF_EMISSION, FLAG_MATERIAL_SORT, FLAG_SOBOL_JITTER = 1, 2, 4, 8, 16
+FLAG_NO_MATERIAL_SORT, FLAG_NO_NEE, FLAG_NO_BSDF_EMISSION, FLAG_MATERIAL_SORT, FLAG_SOBOL_JITTER, FLAG_SOBOL_PATH = 1, 2, 4, 8, 16, 32
 
 NODE_DTYPE = np.dtype([("p", "<f4", (3,)), ("e", "u1", (3,)), ("imask", "u1"), ("child_base", "<u4"), ("tri_base", "<u4"), ("meta", "u1", (8,)),
                        ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])

@@ -75,6 +75,7 @@ enum {
     FOUNDATION_PT_FLAG_NO_NEE = 1u << 1,           /* BSDF sampling only (oracle self-checks)                  */
     FOUNDATION_PT_FLAG_NO_BSDF_EMISSION = 1u << 2, /* NEE only: emitters hit by BSDF rays after bounce 0 add nothing */
     FOUNDATION_PT_FLAG_SOBOL_JITTER = 1u << 4,     /* sub-pixel positions from a per-pixel scrambled Sobol (0,2)-sequence instead of PCG32 */
+    FOUNDATION_PT_FLAG_SOBOL_PATH = 1u << 5,       /* light-point and BSDF-direction samples of every path vertex from padded, Owen-scrambled (0,2)-sequences */
     FOUNDATION_PT_FLAG_MATERIAL_SORT = 1u << 3     /* counting-sort live paths by material id before shading.  Off by default: with ONE
                                                       surface model for all materials the sort costs 8-14 % of a pass and buys nothing
                                                       (measured); results are identical either way.              */

@@ -625,7 +625,7 @@ void orc_render(void* p, uint32_t width, uint32_t height, uint64_t seed, uint32_
     const Scene& s = *(Scene*)p;
     if (!tile) tile = 32;
     PtShadeConsts sc; sc.lights = s.lights.data(); sc.num_lights = (uint32_t)s.lights.size(); sc.light_area = s.light_area;
-    sc.ray_eps = s.ray_eps; sc.flags = flags; sc.max_bounces = max_bounces; sc.bg[0] = bg[0]; sc.bg[1] = bg[1]; sc.bg[2] = bg[2];
+    sc.ray_eps = s.ray_eps; sc.flags = flags; sc.seed = seed; sc.max_bounces = max_bounces; sc.bg[0] = bg[0]; sc.bg[1] = bg[1]; sc.bg[2] = bg[2];
     std::atomic<uint64_t> n_ext{0}, n_sh{0};
     parallel_for((uint64_t)width * height, nthreads, 256, [&](uint64_t b, uint64_t e, int) {
         Counters c; uint64_t ext = 0, shd = 0;
@@ -685,6 +685,8 @@ uint32_t orc_pcg_raw(uint64_t initstate, uint64_t initseq, uint32_t n, uint32_t*
 }
 uint64_t orc_morton(const float* c, const float* lo, const float* inv) { return pt_morton63(pt_mk(c[0], c[1], c[2]), pt_mk(lo[0], lo[1], lo[2]), pt_mk(inv[0], inv[1], inv[2])); }
 void orc_sobol02(uint32_t sample, uint32_t k0, uint32_t k1, float* x, float* y) { pt_sobol02(sample, k0, k1, x, y); }
+void orc_sobol02_padded(uint32_t sample, uint64_t key, float* x, float* y) { pt_sobol02_padded(sample, key, x, y); }
+uint64_t orc_path_dim_key(uint64_t seed, uint32_t pixel, uint32_t bounce, uint32_t which) { return pt_path_dim_key(seed, pixel, bounce, which); }
 int orc_hw_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -78,6 +78,8 @@ def lib() -> C.CDLL:
         L.orc_morton.restype = C.c_uint64
         L.orc_morton.argtypes = [C.c_void_p] * 3
         L.orc_sobol02.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_sobol02_padded.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.orc_path_dim_key.restype = C.c_uint64; L.orc_path_dim_key.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_hw_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -211,3 +213,11 @@ def sobol02(sample, k0=0, k1=0):
 
 def hw_threads():
     return lib().orc_hw_threads()
+
+
+def sobol02_padded(sample, key):
+    x = C.c_float(); y = C.c_float(); lib().orc_sobol02_padded(sample, key, C.byref(x), C.byref(y)); return x.value, y.value
+
+
+def path_dim_key(seed, pixel, bounce, which):
+    return int(lib().orc_path_dim_key(seed, pixel, bounce, which))

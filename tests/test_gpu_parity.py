@@ -70,7 +70,7 @@ def test_device_resident_path_equals_host_path(pair):
     assert st.kernel_launches >= 1 and st.last_ms > 0
 
 
-@pytest.mark.parametrize("flags", [0, pt.FLAG_MATERIAL_SORT, pt.FLAG_SOBOL_JITTER])
+@pytest.mark.parametrize("flags", [0, pt.FLAG_MATERIAL_SORT, pt.FLAG_SOBOL_JITTER, pt.FLAG_SOBOL_PATH, pt.FLAG_SOBOL_JITTER | pt.FLAG_SOBOL_PATH])
 def test_image_matches_oracle(pair, flags):
     """B1-B7: the wavefront loop (queues, compaction, material sort) against one scalar loop per path."""
     name, sc, _, orc = pair

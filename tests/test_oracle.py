@@ -376,3 +376,41 @@ def test_sobol_jitter_lowers_pixel_variance_and_keeps_the_mean():
     a = o.render(24, 24, 3, 0, spp, 2, flags=0)[..., :3] / spp
     b = o.render(24, 24, 3, 0, spp, 2, flags=16)[..., :3] / spp
     assert abs(a.mean() - b.mean()) / a.mean() < 0.05 and not np.array_equal(a, b)
+
+
+def test_padded_sobol_path_dimensions_are_nets_and_decorrelated():
+    """PT_FLAG_SOBOL_PATH: every (pixel, bounce, decision) key gives a sequence whose aligned 2^k-sample blocks are (0,2)-nets (index
+    shuffle + Owen scrambling of both coordinates are nested permutations), and two decisions of the same vertex fill the joint
+    domain like independent samples (padding), not like one sequence XOR-ed with itself."""
+    keys = (0x123456789abcdef, orc.path_dim_key(7, 100, 0, 0), orc.path_dim_key(7, 100, 3, 1))
+    assert len(set(keys)) == 3
+    for key in keys:
+        for k in (3, 6, 8):
+            n = 1 << k
+            for start in (0, 3 * n):
+                p = np.asarray([orc.sobol02_padded(start + i, key) for i in range(n)])
+                assert p.min() >= 0.0 and p.max() < 1.0
+                for a in range(k + 1):
+                    cells = np.floor(p[:, 0] * (1 << a)).astype(int) * (1 << (k - a)) + np.floor(p[:, 1] * (1 << (k - a))).astype(int)
+                    assert len(set(cells.tolist())) == n, (hex(key), k, start, a)
+    a = np.asarray([orc.sobol02_padded(i, orc.path_dim_key(7, 100, 0, 0)) for i in range(1024)])
+    b = np.asarray([orc.sobol02_padded(i, orc.path_dim_key(7, 100, 0, 1)) for i in range(1024)])
+    assert abs(np.corrcoef(a[:, 0], b[:, 0])[0, 1]) < 0.1 and abs(np.corrcoef(a[:, 1], b[:, 1])[0, 1]) < 0.1
+    joint = np.floor(a[:, 0] * 32).astype(int) * 32 + np.floor(b[:, 0] * 32).astype(int)
+    assert 560 < len(set(joint.tolist())) < 740        # independent points occupy ~647 of 1024 cells; a shared sequence would occupy 32 or 1024
+
+
+def test_sobol_path_dimensions_keep_the_mean_and_do_not_raise_the_error():
+    sc = scenes.cornell_box(24, 24)
+    o = OracleScene(sc)
+    ref = o.render(24, 24, 99, 0, 1024, 3, flags=0)[..., :3] / 1024
+    err = {}
+    for fl in (0, 32, 48):
+        e = []
+        for seed in range(4):
+            im = o.render(24, 24, seed, 0, 32, 3, flags=fl)[..., :3] / 32
+            assert abs(im.mean() - ref.mean()) / ref.mean() < 0.08, (fl, seed)
+            e.append(float(np.sqrt(np.mean((im - ref) ** 2))))
+        err[fl] = float(np.mean(e))
+    assert err[32] < 1.1 * err[0] and err[48] < 0.8 * err[0], err
+    assert not np.array_equal(o.render(24, 24, 1, 0, 2, 3, flags=0), o.render(24, 24, 1, 0, 2, 3, flags=32))
