@@ -193,8 +193,14 @@ PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax
 // node visit.  A lane whose node produced a single triangle therefore does both in one iteration, lanes with more pending
 // triangles spend extra iterations in the (short) triangle block only; the triangles of a node are always tested before
 // any of its children is visited, so the visit order — and the node / triangle counters — equal the oracle's.
-template <bool ANY, bool TWO_LEVEL, class Counter>
-PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHitRec* best, Counter& cnt) {
+// The group stack is any type with put(i, e) / get(i): a plain array here, optionally shared memory for the first entries in the kernels.
+struct PtArrayStack {
+    PtU2 a[PT_STACK_SIZE];
+    PT_HDM void put(int i, const PtU2& e) { a[i] = e; }
+    PT_HDM PtU2 get(int i) const { return a[i]; }
+};
+template <bool ANY, bool TWO_LEVEL, class Counter, class Stack>
+PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, Stack& stack, PtHitRec* best, Counter& cnt) {
     const bool do_tri = s->tg.y != 0;
     const bool leaf_tri = !TWO_LEVEL || s->in_blas;
     // the node visit of this step happens iff the lane has no triangle left after (at most) one test; whether it does is known
@@ -220,7 +226,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
         nbase = s->node_base;
         if (s->ng.y & 0xff000000u) {
             if (s->sp >= PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
-            stack[s->sp++] = s->ng;
+            stack.put(s->sp++, s->ng);
         }
     }
     const PtU4* np = sc.nodes + 5 * (size_t)(nbase + child);
@@ -232,9 +238,9 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
         } else {
             // TLAS leaf: enter the instance.  Save the remaining groups, push the return sentinel.
             if (s->sp + 3 > PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
-            if (s->ng.y & 0xff000000u) stack[s->sp++] = s->ng;   // popped last: the node's remaining instances come before its internal children
-            if (s->tg.y) stack[s->sp++] = s->tg;
-            PtU2 sentinel; sentinel.x = PT_NONE; sentinel.y = 0; stack[s->sp++] = sentinel;
+            if (s->ng.y & 0xff000000u) stack.put(s->sp++, s->ng);   // popped last: the node's remaining instances come before its internal children
+            if (s->tg.y) stack.put(s->sp++, s->tg);
+            PtU2 sentinel; sentinel.x = PT_NONE; sentinel.y = 0; stack.put(s->sp++, sentinel);
             const PtU4* ip = sc.instances + 7 * (size_t)(s->tg.x + k);
             PtU4 m0 = pt_load4(ip), m1 = pt_load4(ip + 1), m2 = pt_load4(ip + 2), m6 = pt_load4(ip + 6);
             float w2o[12] = {pt_u2f(m0.x), pt_u2f(m0.y), pt_u2f(m0.z), pt_u2f(m0.w), pt_u2f(m1.x), pt_u2f(m1.y),
@@ -256,7 +262,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
     // both groups empty: pop the next group (a node group keeps its hit bits in the top byte, a triangle group has none)
     while (!s->tg.y && !(s->ng.y & 0xff000000u)) {
         if (s->sp == 0) return PT_STEP_DONE;
-        PtU2 e = stack[--s->sp];
+        PtU2 e = stack.get(--s->sp);
         if (TWO_LEVEL && e.x == PT_NONE && e.y == 0) {   // leaving an instance
             s->r = s->world; s->in_blas = false; s->node_base = sc.tlas_base; s->tri_base = 0; s->cur_inst = PT_NONE;
             continue;
@@ -270,7 +276,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, PtU2* stack, PtHit
 template <bool ANY, bool TWO_LEVEL, class Counter>
 PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best, Counter& cnt) {
     PtTravState s;
-    PtU2 stack[PT_STACK_SIZE];
+    PtArrayStack stack;
     pt_trav_init<TWO_LEVEL>(&s, o, d, tmin, tmax, best, sc.tlas_base);
     while (pt_trav_step<ANY, TWO_LEVEL>(sc, &s, stack, best, cnt) == PT_STEP_RUNNING) {}
     return !s.overflow;
