@@ -570,28 +570,11 @@ struct PtDevCounters { unsigned long long nodes, tris, insts; };
 // file (measured: forcing 10 or 12 CTAs spills and is 25-40 % slower).  Two-level kernels carry the world ray as well and need 80
 // registers: 6 CTAs (forcing 64 registers spills and costs 12 %).
 #define PT_TRACE_MIN_BLOCKS(two_level) ((two_level) ? 6 : 8)
-// experiment switch: the first PT_SMEM_STACK entries of the group stack in shared memory (entry i of thread t at [i][t]: conflict free)
-#ifndef PT_SMEM_STACK
-#define PT_SMEM_STACK 0
-#endif
-#if PT_SMEM_STACK > 0
-struct PtHybridStack {
-    PtU2 a[PT_STACK_SIZE];
-    PtU2* sm;
-    __device__ __forceinline__ void put(int i, const PtU2& e) { if (i < PT_SMEM_STACK) sm[i * 128] = e; else a[i] = e; }
-    __device__ __forceinline__ PtU2 get(int i) const { return i < PT_SMEM_STACK ? sm[i * 128] : a[i]; }
-};
-#endif
 template <bool ANY, bool TWO_LEVEL, class Counter, class Job>
 __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, unsigned long long n, unsigned long long* work_counter, uint32_t* status,
                                               Counter& cnt, int fetch_thresh) {
     PtTravState st;
-#if PT_SMEM_STACK > 0
-    __shared__ PtU2 s_stack[PT_SMEM_STACK][128];
-    PtHybridStack stack; stack.sm = &s_stack[0][threadIdx.x];
-#else
     PtArrayStack stack;
-#endif
     PtHitRec best;
     bool active = false, drained = false;   // drained: the global queue is empty (warp-uniform once set)
     unsigned long long idx = 0;
