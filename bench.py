@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--log2-rays", type=int, default=26)
     ap.add_argument("--spp", type=int, default=64, help="samples per pixel per render step of the spp/s measurement (0 = skip)")
     ap.add_argument("--bounces", type=int, default=8)
-    ap.add_argument("--cpu-log2-rays", type=int, default=22, help="bounded CPU-baseline sample")
+    ap.add_argument("--cpu-log2-rays", type=int, default=26, help="CPU-baseline / parity sample (default: the whole 2^26 ray set, ~5 s on 16 host threads)")
+    ap.add_argument("--ref-log2-rays", type=int, default=23, help="rays per step of the --impl reference arm (bounded sample of the same set)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     return ap.parse_args()
@@ -129,7 +130,7 @@ def run_reference(a, rank, world):
     sc = scenes.fractal_terrain(n=a.terrain_n)
     orc = OracleScene(sc)
     lo, hi = scenes.scene_bounds(sc)
-    n = 1 << min(a.cpu_log2_rays, 20)
+    n = 1 << min(a.ref_log2_rays, a.log2_rays)
     rays = scenes.incoherent_rays(lo, hi, n, seed=4)
     cores = hw_threads()
     for _ in range(a.warmup):
@@ -267,7 +268,10 @@ def main():
         oh, oi, cnt = orc.trace_closest(rays[:ncpu], counters=True)
         cpu_s = time.perf_counter() - t0
         mismatches = int((gh["prim"] != oh["prim"]).sum())
-        max_ulp = int(np.abs(gh["t"].view(np.uint32).astype(np.int64) - oh["t"].view(np.uint32).astype(np.int64)).max())
+        max_ulp = 0
+        for c0 in range(0, ncpu, 1 << 22):                                          # chunked: no 64-bit temporaries of the whole set
+            sl = slice(c0, min(ncpu, c0 + (1 << 22)))
+            max_ulp = max(max_ulp, int(np.abs(gh["t"][sl].view(np.uint32).astype(np.int64) - oh["t"][sl].view(np.uint32).astype(np.int64)).max()))
         mismatches += int((e2e_hits["prim"][:ncpu] != oh["prim"]).sum())           # the e2e path must agree too
         nb = 128
         bh, _ = orc.trace_closest(rays[:nb], brute=True)

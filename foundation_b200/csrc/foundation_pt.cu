@@ -249,6 +249,15 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
     uint32_t zero = 0;
     PT_CK(cudaMemcpyAsync(refs_a.p, &zero, 4, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t m = 1, level_start = 0, prim_total = 0;
+    {   // top of the tree: all levels of at most PT_TOP_NODES wide nodes in one single-block launch
+        PT_LAUNCH(ctx, k_collapse_top, 1, PT_TOP_NODES, b, refs_a.as<uint32_t>(), refs_b.as<uint32_t>(), max_leaf, d_bp, nodes_tmp.as<PtNode8>(), out->leaf_seq.as<uint32_t>(),
+                  totals.as<uint32_t>());
+        uint32_t st[4];
+        PT_CK(cudaMemcpyAsync(st, totals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        PT_CK(cudaStreamSynchronize(ctx->stream));
+        m = st[0]; level_start = st[1]; prim_total = st[2];
+        if (st[3]) std::swap(refs_a, refs_b);
+    }
     size_t cap = 0;
     while (m > 0) {
         if (cap < m) {

@@ -484,6 +484,30 @@ __global__ void __launch_bounds__(128) k_collapse_emit(PtBvh2 b, const uint32_t*
                          leaf_seq);
     }
 }
+// The first levels of the collapse hold 1, ~6, ~40, ... nodes: as separate launches each level is a select kernel, two 3-kernel scans, an
+// emit kernel and a host round trip for the level's totals — ~100 us of pure latency per level.  One block walks all levels of at most
+// PT_TOP_NODES nodes instead (one thread per wide node, block-wide scans, the same numbering as the level-synchronous path) and leaves
+// {m, level_start, prim_total, which refs buffer is current} for the host to carry on from.
+#define PT_TOP_NODES 256
+__global__ void __launch_bounds__(PT_TOP_NODES) k_collapse_top(PtBvh2 b, uint32_t* refs_a, uint32_t* refs_b, uint32_t max_leaf, const PtBuildParams* bp, PtNode8* nodes,
+                                                               uint32_t* leaf_seq, uint32_t* state) {
+    const float pad = bp->pad;
+    const uint32_t tid = threadIdx.x;
+    uint32_t m = 1, level_start = 0, prim_total = 0, parity = 0;
+    uint32_t *cur = refs_a, *nxt = refs_b;
+    while (m > 0 && m <= PT_TOP_NODES && level_start + m <= b.n) {
+        uint32_t s[8], ni = 0, np = 0;
+        if (tid < m) pt_collapse_select(b, cur[tid], max_leaf, s, &ni, &np);
+        uint32_t tot_i, tot_p;
+        const uint32_t off_i = pt_block_excl_scan(ni, &tot_i);
+        const uint32_t off_p = pt_block_excl_scan(np, &tot_p);
+        if (tid < m) pt_collapse_emit(b, cur[tid], s, max_leaf, pad, level_start + m + off_i, prim_total + off_p, &nodes[level_start + tid], nxt + off_i, leaf_seq);
+        __syncthreads();                                  // next level's refs (global memory) are visible to the whole block
+        level_start += m; prim_total += tot_p; m = tot_i; parity ^= 1u;
+        uint32_t* t = cur; cur = nxt; nxt = t;
+    }
+    if (tid == 0) { state[0] = m; state[1] = level_start; state[2] = prim_total; state[3] = parity; }
+}
 __global__ void __launch_bounds__(256) k_write_tris(PtMeshRaw m, const uint32_t* order, const uint32_t* leaf_seq, PtTri* tris) {
     for (uint32_t k = pt_gtid(); k < m.ntris; k += pt_gsize()) {
         uint32_t i = order[leaf_seq[k]];

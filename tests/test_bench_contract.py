@@ -13,7 +13,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_reference_arm_prints_one_json_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--terrain-n", "96", "--steps", "2", "--warmup", "1", "--cpu-log2-rays", "14"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--terrain-n", "96", "--steps", "2", "--warmup", "1", "--ref-log2-rays", "14"],
                          capture_output=True, text=True, check=True, cwd=ROOT).stdout.strip().splitlines()
     assert len(out) == 1
     line = json.loads(out[0])

@@ -366,3 +366,43 @@ def test_pathological_rays_terminate_and_match_oracle(gpu):
     assert np.array_equal(gh["prim"], oh["prim"]) and gh.tobytes() == oh.tobytes()
     assert np.array_equal(tr.trace_any(rays), orc.trace_any(rays))
     tr.close()
+
+
+@pytest.mark.parametrize("ntris", [1, 2, 3, 255, 256, 257, 511, 512, 513, 1025, 70001])
+def test_build_sizes_around_the_refit_tiles(gpu, ntris):
+    """A4: the tiled refit (256 sorted leaves per block, rounds in shared memory, upper levels in a second kernel) must give the oracle's
+    nodes byte for byte for triangle counts below, at and just above tile multiples, and for a mesh whose Morton keys are all equal
+    except for a few (deep, chain-like radix tree: many rounds inside one tile)."""
+    n = int(np.ceil(np.sqrt(ntris / 2.0))) + 1
+    base = scenes.fractal_terrain(n=n, width=32, height=32, with_light=False)
+    m = base.meshes[0]
+    idx = np.ascontiguousarray(m.indices[:ntris]); mat = np.ascontiguousarray(m.material_ids[:ntris])
+    assert idx.shape[0] == ntris
+    sc = scenes.Scene(f"terrain_first_{ntris}", [scenes.Mesh(m.positions, idx, mat)], base.materials, None, base.view, base.proj, 32, 32)
+    tr = pt.PathTracer(32, 32); tr.load(sc)
+    orc = OracleScene(sc)
+    gn, gt, go = tr.blas_download(0); on, ot, oo = orc.blas(0)
+    assert np.array_equal(go, oo) and gn.tobytes() == on.tobytes() and gt.tobytes() == ot.tobytes(), ntris
+    lo, hi = scenes.scene_bounds(sc)
+    rays = scenes.incoherent_rays(lo, hi, 4096, 9)
+    gh, gi = tr.trace_closest(rays); oh, oi = orc.trace_closest(rays)
+    assert gh.tobytes() == oh.tobytes()
+    tr.close()
+
+
+def test_build_of_a_chain_like_radix_tree(gpu):
+    """600 copies of one triangle (identical Morton keys: the radix tree is decided by the index tie-break) plus a few far-away ones."""
+    rng = np.random.default_rng(5)
+    tri = np.asarray([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    pos = np.concatenate([np.tile(tri, (600, 1)), (rng.uniform(-50, 50, (7, 1, 3)) + tri[None]).reshape(-1, 3).astype(np.float32)])
+    idx = np.arange(pos.shape[0], dtype=np.uint32).reshape(-1, 3)
+    base = scenes.cornell_box(32, 32)
+    sc = scenes.Scene("chain", [scenes.Mesh(np.ascontiguousarray(pos), idx, np.zeros(idx.shape[0], np.uint32))], base.materials, None, base.view, base.proj, 32, 32)
+    tr = pt.PathTracer(32, 32); tr.load(sc)
+    orc = OracleScene(sc)
+    gn, gt, go = tr.blas_download(0); on, ot, oo = orc.blas(0)
+    assert np.array_equal(go, oo) and gn.tobytes() == on.tobytes() and gt.tobytes() == ot.tobytes()
+    rays = scenes.incoherent_rays(np.full(3, -2.0), np.full(3, 2.0), 4096, 10)
+    gh, gi = tr.trace_closest(rays); oh, oi = orc.trace_closest(rays)
+    assert gh.tobytes() == oh.tobytes()
+    tr.close()
