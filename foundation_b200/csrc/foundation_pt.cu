@@ -237,7 +237,9 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
         DevBuf up_list, up_count;   // freed stream-ordered when the scope ends
         PT_CK(up_list.alloc((size_t)n * 4)); PT_CK(up_count.alloc(16));
         PT_CK(cudaMemsetAsync(up_count.p, 0, 4, ctx->stream));
-        PT_LAUNCH(ctx, k_refit, grid_for(ctx, n, PT_REFIT_TILE, 8), PT_REFIT_TILE, b, d_prim_box, vals.as<uint32_t>(), up_list.as<uint32_t>(), up_count.as<uint32_t>(), max_leaf);
+        static int refit_blocks = 0;     // resident blocks per SM (shared-memory bound): the grid is exactly one wave, tiles are strided over it
+        if (!refit_blocks && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&refit_blocks, k_refit, PT_REFIT_TILE, 0) != cudaSuccess || refit_blocks < 1)) { cudaGetLastError(); refit_blocks = 4; }
+        PT_LAUNCH(ctx, k_refit, grid_for(ctx, n, PT_REFIT_TILE, (uint32_t)refit_blocks), PT_REFIT_TILE, b, d_prim_box, vals.as<uint32_t>(), up_list.as<uint32_t>(), up_count.as<uint32_t>(), max_leaf);
         if (n > 1) PT_LAUNCH(ctx, k_refit_up, grid_for(ctx, n / 16 + 1, 128, 8), 128, b, up_list.as<uint32_t>(), up_count.as<uint32_t>(), flags.as<uint32_t>(), max_leaf);
     }
     // collapse, level by level

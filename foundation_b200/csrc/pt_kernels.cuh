@@ -305,7 +305,9 @@ __device__ __forceinline__ PtBox pt_ldcg_box(const PtBox* p) {
 // for 10 M triangles (5.8 % of DRAM peak).  Results of the tile are written back coalesced at the end.
 // The roots of the tile's maximal local subtrees are appended to a global list; k_refit_up continues from them with the global
 // protocol (device fence, global arrival counter, sibling read back from L2): a few threads per tile, log-many levels.
+#ifndef PT_REFIT_TILE
 #define PT_REFIT_TILE 256
+#endif
 __device__ __forceinline__ PtBox pt_lds_box(const PtBox* p) {   // volatile: written by another thread of the block in an earlier round
     const volatile float* f = reinterpret_cast<const volatile float*>(p);
     PtBox b; b.lox = f[0]; b.loy = f[1]; b.loz = f[2]; b.hix = f[3]; b.hiy = f[4]; b.hiz = f[5];
