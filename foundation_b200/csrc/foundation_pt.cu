@@ -118,7 +118,7 @@ struct foundation_pt_context {
     std::vector<foundation_pt_instance> insts; bool has_insts = false;
 
     // committed scene
-    bool committed = false, two_level = false;
+    bool committed = false, two_level = false, render_pending = false;
     DevBuf d_nodes_all, d_tris_all, d_instances, d_inst_in, d_mesh_info, d_mats, d_lights;
     std::vector<PtMeshInfo> mesh_info;
     DevBuf d_tlas_order; uint32_t tlas_nodes = 0, num_inst = 0;
@@ -364,7 +364,10 @@ int32_t launch_trace(Ctx* ctx, const float4* rays, uint64_t n, float4* hits, uin
     return 0;
 }
 
-void begin_call(Ctx* ctx) { ctx->call_launches = 0; cudaEventRecord(ctx->ev0, ctx->stream); }
+// An asynchronous render still in flight is settled (foundation_pt_wait) before any other call touches the context: every entry point
+// except render_async behaves as if the context were idle.
+void settle(Ctx* ctx);
+void begin_call(Ctx* ctx) { settle(ctx); ctx->call_launches = 0; cudaEventRecord(ctx->ev0, ctx->stream); }
 int32_t end_call(Ctx* ctx) {
     PT_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     PT_CK(cudaStreamSynchronize(ctx->stream));
@@ -462,6 +465,9 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
     } catch (const std::bad_alloc&) { if (ctxexpr) (ctxexpr)->err = "host allocation failed"; return FOUNDATION_PT_ERR_OOM; } \
     catch (const std::exception& e) { if (ctxexpr) (ctxexpr)->err = e.what(); return FOUNDATION_PT_ERR_STATE; }         \
     catch (...) { if (ctxexpr) (ctxexpr)->err = "unknown exception"; return FOUNDATION_PT_ERR_STATE; }
+
+extern "C" int32_t foundation_pt_wait(foundation_pt_context* ctx);
+namespace { void settle(Ctx* ctx) { if (ctx->render_pending) foundation_pt_wait(ctx); } }
 
 extern "C" {
 
@@ -775,17 +781,21 @@ int32_t foundation_pt_camera_set(foundation_pt_context* ctx, const float view[16
 
 int32_t foundation_pt_partition_set(foundation_pt_context* ctx, uint32_t rank, uint32_t count, uint32_t tile_size) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (count == 0 || rank >= count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "partition_set: rank must be < count");
     ctx->part_rank = rank; ctx->part_count = count; ctx->part_tile = tile_size ? tile_size : 32;
     ctx->wave_ready = false;
     return FOUNDATION_PT_OK;
 }
 
-int32_t foundation_pt_render(foundation_pt_context* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces) {
+// render = render_async + wait.  The asynchronous pair only enqueues the wavefront loop on the context's stream (no host round trip
+// happens inside the loop: the bounce count is fixed and the queue sizes live on the device), so a host Draw() can overlap its own work.
+int32_t foundation_pt_render_async(foundation_pt_context* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
     if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "render: scene not committed");
     if (!ctx->cam_set) return ctx->fail(FOUNDATION_PT_ERR_STATE, "render: camera not set");
     if (max_bounces > 64) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "render: max_bounces > 64");
+    if (ctx->render_pending) return ctx->fail(FOUNDATION_PT_ERR_STATE, "render_async: the previous asynchronous render has not been waited for");
     PT_TRY
     cudaSetDevice(ctx->device);
     int32_t rc = setup_wave(ctx);
@@ -797,8 +807,21 @@ int32_t foundation_pt_render(foundation_pt_context* ctx, uint32_t sample_begin, 
         rc = ctx->two_level ? render_impl<true>(ctx, sample_begin, sample_count, max_bounces) : render_impl<false>(ctx, sample_begin, sample_count, max_bounces);
         if (rc) return rc;
     }
-    rc = end_call(ctx);
-    if (rc) return rc;
+    PT_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->render_pending = true;
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_wait(foundation_pt_context* ctx) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if (!ctx->render_pending) return FOUNDATION_PT_OK;      // nothing in flight: every other entry point is blocking
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    ctx->render_pending = false;
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.last_ms = ms; ctx->stats.kernel_launches = ctx->call_launches; ctx->stats.total_launches = ctx->total_launches;
     PtWaveCounters c;
     PT_CK(cudaMemcpy(&c, ctx->w_ctr.p, sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.rays_extend = c.total_extend; ctx->stats.rays_shadow = c.total_shadow;
@@ -806,8 +829,15 @@ int32_t foundation_pt_render(foundation_pt_context* ctx, uint32_t sample_begin, 
     PT_CATCH(ctx)
 }
 
+int32_t foundation_pt_render(foundation_pt_context* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces) {
+    int32_t rc = foundation_pt_render_async(ctx, sample_begin, sample_count, max_bounces);
+    if (rc) return rc;
+    return foundation_pt_wait(ctx);
+}
+
 int32_t foundation_pt_read_accum(foundation_pt_context* ctx, float* rgba, size_t size_bytes) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     size_t need = (size_t)ctx->cfg.width * ctx->cfg.height * 16;
     if (!rgba || size_bytes < need) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "read_accum: buffer too small");
     cudaSetDevice(ctx->device);
@@ -819,6 +849,7 @@ int32_t foundation_pt_read_accum(foundation_pt_context* ctx, float* rgba, size_t
 
 int32_t foundation_pt_write_accum(foundation_pt_context* ctx, const float* rgba, size_t size_bytes) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     size_t need = (size_t)ctx->cfg.width * ctx->cfg.height * 16;
     if (!rgba || size_bytes < need) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "write_accum: buffer too small");
     cudaSetDevice(ctx->device);
@@ -830,6 +861,7 @@ int32_t foundation_pt_write_accum(foundation_pt_context* ctx, const float* rgba,
 
 int32_t foundation_pt_resolve_rgba8(foundation_pt_context* ctx, uint8_t* rgba8, size_t size_bytes) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     uint32_t n = ctx->cfg.width * ctx->cfg.height;
     if (!rgba8 || size_bytes < (size_t)n * 4) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "resolve_rgba8: buffer too small");
     if (!ctx->d_accum.p) return ctx->fail(FOUNDATION_PT_ERR_STATE, "resolve_rgba8: nothing rendered");
@@ -845,6 +877,7 @@ int32_t foundation_pt_resolve_rgba8(foundation_pt_context* ctx, uint8_t* rgba8, 
 
 int32_t foundation_pt_accum_device_ptr(foundation_pt_context* ctx, void** out_device_ptr, size_t* out_size_bytes) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (!out_device_ptr) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "accum_device_ptr: NULL out pointer");
     cudaSetDevice(ctx->device);
     size_t need = (size_t)ctx->cfg.width * ctx->cfg.height * 16;

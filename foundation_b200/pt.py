@@ -53,6 +53,8 @@ SYMBOLS = {
     "foundation_pt_camera_set": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "foundation_pt_partition_set": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "foundation_pt_render": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "foundation_pt_render_async": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "foundation_pt_wait": (C.c_int32, [C.c_void_p]),
     "foundation_pt_read_accum": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "foundation_pt_write_accum": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "foundation_pt_resolve_rgba8": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -200,6 +202,13 @@ class PathTracer:
     # -- render
     def render(self, sample_begin: int, sample_count: int, max_bounces: int):
         self._check(self._lib.foundation_pt_render(self._ctx, sample_begin, sample_count, max_bounces))
+
+    def render_async(self, sample_begin: int, sample_count: int, max_bounces: int):
+        """Enqueue a render and return at once; `wait()` (or any other call) completes it."""
+        self._check(self._lib.foundation_pt_render_async(self._ctx, sample_begin, sample_count, max_bounces))
+
+    def wait(self):
+        self._check(self._lib.foundation_pt_wait(self._ctx))
 
     def read_accum(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:

@@ -169,6 +169,12 @@ FOUNDATION_PT_API int32_t foundation_pt_partition_set(foundation_pt_context* ctx
  * Adds samples [sample_begin, sample_begin + sample_count) of every owned pixel to the accumulation buffer.
  * sample_begin == 0 clears the buffer first. */
 FOUNDATION_PT_API int32_t foundation_pt_render(foundation_pt_context* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces);
+/* Asynchronous form (SURVEY.md section 8b "an async variant (render_async + wait) is optional"): render_async only enqueues the same work on
+ * the context's stream and returns; wait blocks until it has finished, fills the stats and reports a traversal-stack overflow exactly like
+ * render.  render == render_async + wait.  Any other entry point called in between first waits, so the context always behaves as if
+ * it were idle (the reference's Draw() is blocking, Renderer.cpp:394; a host that wants to overlap its own per-frame work uses this pair). */
+FOUNDATION_PT_API int32_t foundation_pt_render_async(foundation_pt_context* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces);
+FOUNDATION_PT_API int32_t foundation_pt_wait(foundation_pt_context* ctx);
 /* Linear radiance SUM (not yet divided by spp) as float4 per pixel, row-major from the top-left; w = sample count. */
 FOUNDATION_PT_API int32_t foundation_pt_read_accum(foundation_pt_context* ctx, float* rgba, size_t size_bytes);
 /* Restores an accumulation buffer saved with read_accum (checkpoint / resume of a progressive render; the

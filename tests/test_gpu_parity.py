@@ -406,3 +406,24 @@ def test_build_of_a_chain_like_radix_tree(gpu):
     gh, gi = tr.trace_closest(rays); oh, oi = orc.trace_closest(rays)
     assert gh.tobytes() == oh.tobytes()
     tr.close()
+
+
+def test_render_async_plus_wait_equals_render(gpu):
+    """render_async enqueues, wait completes; any other entry point in between waits implicitly; a second render_async before the wait is a
+    state error.  The frame equals the blocking render's bit for bit."""
+    sc = SMALL_SCENES["cornell"]()
+    a = pt.PathTracer(sc.width, sc.height, seed=3, background=sc.background); a.load(sc)
+    b = pt.PathTracer(sc.width, sc.height, seed=3, background=sc.background); b.load(sc)
+    a.render(0, 4, 4)
+    b.render_async(0, 2, 4)
+    with pytest.raises(pt.FoundationPtError) as e:
+        b.render_async(2, 2, 4)
+    assert e.value.status == pt.ERR_STATE
+    b.wait()
+    st = b.stats()
+    assert st.rays_extend > 0 and st.last_ms > 0
+    b.render_async(2, 2, 4)
+    img = b.read_accum()                     # no explicit wait: read_accum settles the pending render first
+    assert np.array_equal(img, a.read_accum())
+    b.wait()                                 # nothing in flight: a no-op
+    a.close(); b.close()
