@@ -184,10 +184,10 @@ inline uint32_t trace_blocks(const Ctx* ctx) {   // persistent grid of the trave
 int32_t scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf& chunk_sums, uint32_t* d_total) {
     uint32_t chunks = (n + PT_SCAN_CHUNK - 1) / PT_SCAN_CHUNK;
     if (chunks == 0) chunks = 1;
-    if (chunk_sums.bytes < (size_t)chunks * 4) PT_CK(chunk_sums.alloc((size_t)chunks * 4 + 1024));
-    PT_LAUNCH(ctx, k_scan_chunks, chunks, PT_SCAN_THREADS, in, out, n, chunk_sums.as<uint32_t>());
-    PT_LAUNCH(ctx, k_scan_sums, 1, 1024, chunk_sums.as<uint32_t>(), chunks, d_total);
-    if (chunks > 1) PT_LAUNCH(ctx, k_scan_add, chunks, PT_SCAN_THREADS, out, n, chunk_sums.as<uint32_t>());
+    const size_t state_bytes = ((size_t)chunks + 1) * 8;          // one status word per tile + the ticket counter
+    if (chunk_sums.bytes < state_bytes) PT_CK(chunk_sums.alloc(state_bytes + 4096));
+    PT_CK(cudaMemsetAsync(chunk_sums.p, 0, state_bytes, ctx->stream));
+    PT_LAUNCH(ctx, k_scan_lookback, chunks, PT_SCAN_THREADS, in, out, n, chunk_sums.as<unsigned long long>(), chunks, d_total);
     return 0;
 }
 

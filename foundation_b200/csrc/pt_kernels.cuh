@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_morton_boxes(const PtBox* prim_box, uin
 }
 
 // ---------------------------------------------------------------------------------------------------
-// exclusive scan of uint32 (two levels: 4096-element chunks, then one block over the chunk sums)
+// exclusive scan of uint32 (single pass over 4096-element tiles, decoupled look-back)
 // ---------------------------------------------------------------------------------------------------
 #define PT_SCAN_THREADS 256
 #define PT_SCAN_ITEMS 16
@@ -149,34 +149,47 @@ __device__ __forceinline__ uint32_t pt_block_excl_scan(uint32_t v, uint32_t* tot
     return res;
 }
 
-__global__ void __launch_bounds__(PT_SCAN_THREADS) k_scan_chunks(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* chunk_sums) {
-    uint32_t base = blockIdx.x * PT_SCAN_CHUNK + threadIdx.x * PT_SCAN_ITEMS;
+// Single-pass exclusive scan (decoupled look-back, Merrill & Garland 2016): one launch instead of chunks + sums + add, every element read
+// and written once.  A tile takes a ticket (so all its predecessors are running or done: the spin below always makes progress), scans
+// its 4096 elements, publishes its aggregate, then warp 0 walks back over the predecessors' 64-bit status words, 32 at a time — flag in the top two
+// bits (1 = aggregate, 2 = inclusive prefix), value in the low 32 — until it meets an inclusive prefix, and publishes its own.
+// state[0 .. tiles) and the ticket at state[tiles] must be zero at launch.
+__global__ void __launch_bounds__(PT_SCAN_THREADS) k_scan_lookback(const uint32_t* in, uint32_t* out, uint32_t n, unsigned long long* state, uint32_t tiles,
+                                                                    uint32_t* grand_total) {
+    __shared__ uint32_t s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(reinterpret_cast<uint32_t*>(state + tiles), 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * PT_SCAN_CHUNK + threadIdx.x * PT_SCAN_ITEMS;
     uint32_t v[PT_SCAN_ITEMS], sum = 0;
 #pragma unroll
     for (int k = 0; k < PT_SCAN_ITEMS; ++k) { uint32_t i = base + k; v[k] = i < n ? in[i] : 0; sum += v[k]; }
     uint32_t total;
     uint32_t excl = pt_block_excl_scan(sum, &total);
+    if (threadIdx.x < 32) {     // warp 0: publish the aggregate, then look back 32 predecessors at a time
+        const uint32_t lane = threadIdx.x;
+        if (lane == 0) atomicExch(&state[tile], ((tile == 0 ? 2ull : 1ull) << 62) | total);
+        uint32_t prefix = 0;
+        if (tile > 0) {
+            for (long long p = (long long)tile - 1 - lane;; p -= 32) {
+                unsigned long long w = 2ull << 62;                       // before tile 0: an inclusive prefix of 0
+                if (p >= 0) do { w = *reinterpret_cast<volatile unsigned long long*>(&state[p]); } while ((w >> 62) == 0ull);
+                const uint32_t done = __ballot_sync(PT_FULL, (w >> 62) == 2ull);     // lanes that found an inclusive prefix (lane 0 = nearest tile)
+                const uint32_t upto = done ? (uint32_t)__ffs(done) - 1u : 31u;
+                prefix += __reduce_add_sync(PT_FULL, lane <= upto ? (uint32_t)w : 0u);
+                if (done) break;
+            }
+            if (lane == 0) atomicExch(&state[tile], (2ull << 62) | (unsigned long long)(prefix + total));
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile == tiles - 1 && grand_total) *grand_total = prefix + total;
+        }
+    }
+    __syncthreads();
+    excl += s_prefix;
 #pragma unroll
     for (int k = 0; k < PT_SCAN_ITEMS; ++k) { uint32_t i = base + k; if (i < n) out[i] = excl; excl += v[k]; }
-    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
-}
-// one block; scans m chunk sums in place (exclusive) and writes the grand total
-__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, uint32_t m, uint32_t* grand_total) {
-    uint32_t carry = 0;
-    for (uint32_t b = 0; b < m; b += 1024) {
-        uint32_t i = b + threadIdx.x;
-        uint32_t v = i < m ? sums[i] : 0, total;
-        uint32_t e = pt_block_excl_scan(v, &total);
-        if (i < m) sums[i] = carry + e;
-        carry += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && grand_total) *grand_total = carry;
-}
-__global__ void __launch_bounds__(PT_SCAN_THREADS) k_scan_add(uint32_t* out, uint32_t n, const uint32_t* chunk_sums) {
-    uint32_t add = chunk_sums[blockIdx.x];
-    uint32_t base = blockIdx.x * PT_SCAN_CHUNK;
-    for (uint32_t k = threadIdx.x; k < PT_SCAN_CHUNK; k += PT_SCAN_THREADS) { uint32_t i = base + k; if (i < n) out[i] += add; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -184,7 +197,9 @@ __global__ void __launch_bounds__(PT_SCAN_THREADS) k_scan_add(uint32_t* out, uin
 // Per pass: per-tile digit histogram -> exclusive scan over [digit][tile] -> stable scatter with a tile-local sort.
 // ---------------------------------------------------------------------------------------------------
 #define PT_RS_THREADS 256
-#define PT_RS_ROUNDS 4
+#ifndef PT_RS_ROUNDS
+#define PT_RS_ROUNDS 5      // keys per thread: 1280-key tiles (measured on the 10 M-key sort: 4 -> 1.23 ms, 5 -> 1.13, 6 -> 1.17, 8 -> 1.31)
+#endif
 #define PT_RS_TILE (PT_RS_THREADS * PT_RS_ROUNDS)
 
 __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_hist(const uint64_t* keys, uint32_t n, int shift, uint32_t* tile_hist, uint32_t num_tiles) {
@@ -201,9 +216,9 @@ __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_hist(const uint64_t* keys,
     tile_hist[threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// Scatter of one pass.  Each CTA sorts its 4096-key tile locally first, so global writes are runs of consecutive keys per digit
+// Scatter of one pass.  Each CTA sorts its tile (PT_RS_TILE keys) locally first, so global writes are runs of consecutive keys per digit
 // (the first version wrote every 8-byte key to its own 32-byte sector and reached 15 % of HBM peak):
-//   1. warp w loads keys [512 w, 512 w + 512) of the tile, 16 per lane, every load coalesced (order in the tile = w, i, lane);
+//   1. warp w loads its 32 * PT_RS_KEYS consecutive keys of the tile, PT_RS_KEYS per lane, every load coalesced (order in the tile = w, i, lane);
 //   2. rank inside the warp: match_any groups equal digits, a per-warp shared counter carries the running count;
 //   3. one pass over the 8 warp counters per digit + a block scan over the 256 digits give every key its tile-local position;
 //   4. keys go to shared memory at that position, are read back in order and written to global_offset[digit] + run index;
