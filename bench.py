@@ -167,7 +167,7 @@ def main():
 
     def barrier():
         if dist:
-            dist.barrier()
+            dist.barrier(device_ids=[local])      # explicit device: no "using the device under current context" warning after the JSON line
         torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
@@ -303,10 +303,10 @@ def main():
             "build": {"build_ms_first": build_first_ms, "build_ms": build_steady_ms, "sort_ms": sort_steady_ms, "nodes8": int(bs.num_nodes8),
                       "device_bytes": int(bs.device_bytes), "mtris_per_s": bs.num_triangles / (build_steady_ms * 1e-3) / 1e6,
                       "hbm_frac_at_450B_per_tri": bs.num_triangles * 450.0 / (build_steady_ms * 1e-3) / 1e9 / peak}}
-    print(json.dumps(line), flush=True)
     barrier()
     if dist:
         dist.destroy_process_group()
+    print(json.dumps(line), flush=True)          # the ONE JSON line, last thing on stdout
 
 
 if __name__ == "__main__":
