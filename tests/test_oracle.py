@@ -414,3 +414,21 @@ def test_sobol_path_dimensions_keep_the_mean_and_do_not_raise_the_error():
         err[fl] = float(np.mean(e))
     assert err[32] < 1.1 * err[0] and err[48] < 0.8 * err[0], err
     assert not np.array_equal(o.render(24, 24, 1, 0, 2, 3, flags=0), o.render(24, 24, 1, 0, 2, 3, flags=32))
+
+
+@pytest.mark.parametrize("rough,metallic,lo,hi", [(0.1, 1.0, 0.99, 1.005), (0.5, 1.0, 0.85, 1.0), (1.0, 0.0, 0.84, 0.95), (0.5, 0.0, 0.86, 0.97)])
+def test_white_furnace(rough, metallic, lo, hi):
+    """spheres and a ground plane with white, emission-free materials inside a uniform environment of radiance 1,
+    32 bounces, BSDF sampling + Russian roulette only (there is no light to sample).  Energy can only be lost, never gained: a polished
+    white metal (F = 1, negligible single-scattering loss) must return the environment exactly; rough GGX loses what single scattering
+    cannot return; the diffuse base loses the (1 - F)(1 - F) coupling.  The bounds bracket what the model gives; a wrong cosine, pdf,
+    roulette weight or a self-intersecting bounce ray moves the mean far outside them."""
+    sc = scenes.sphere_field(num_spheres=12, subdiv=2, width=48, height=27)
+    mats = sc.materials.copy()
+    mats[:, 0:3] = 1.0; mats[:, 3] = rough; mats[:, 4:7] = 0.0; mats[:, 7] = metallic
+    sc2 = scenes.Scene("furnace", sc.meshes, mats, sc.instances, sc.view, sc.proj, 48, 27, (1.0, 1.0, 1.0))
+    o = OracleScene(sc2)
+    spp = 64
+    img = o.render(48, 27, 5, 0, spp, 32, background=(1.0, 1.0, 1.0))[..., :3] / spp
+    assert lo <= img.mean() <= hi, (rough, metallic, float(img.mean()))
+    assert img.max() <= 1.15, float(img.max())                     # per-pixel 64-spp noise only
