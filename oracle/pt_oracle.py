@@ -42,7 +42,10 @@ def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "libpt_oracle.so")
-        if not os.path.exists(so) or os.environ.get("PT_ORACLE_REBUILD"):
+        alt = os.environ.get("PT_ORACLE_LIB")          # e.g. the -fsanitize=address,undefined build of `make -C oracle asan`
+        if alt:
+            so = alt
+        elif not os.path.exists(so) or os.environ.get("PT_ORACLE_REBUILD"):
             build()
         else:
             try:

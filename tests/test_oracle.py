@@ -5,6 +5,7 @@ import hashlib
 import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -432,3 +433,46 @@ def test_white_furnace(rough, metallic, lo, hi):
     img = o.render(48, 27, 5, 0, spp, 32, background=(1.0, 1.0, 1.0))[..., :3] / spp
     assert lo <= img.mean() <= hi, (rough, metallic, float(img.mean()))
     assert img.max() <= 1.15, float(img.max())                     # per-pixel 64-spp noise only
+
+
+def test_oracle_under_address_and_undefined_behaviour_sanitizers(tmp_path):
+    """the checker itself is checked.  The oracle is rebuilt with -fsanitize=address,undefined and drives a flat scene,
+    an instanced scene and the degenerate mesh through build, both traversals, exhaustive search and a render in a child process."""
+    cxx = asan = None
+    for cand in (os.environ.get("CXX"), "g++", "/usr/bin/g++"):          # the first compiler that ships the sanitizer runtime
+        if not cand:
+            continue
+        try:
+            p = subprocess.run([cand, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+        except OSError:
+            continue
+        if os.path.isabs(p) and os.path.exists(p):
+            cxx, asan = cand, p
+            break
+    if not asan:
+        pytest.skip("no libasan in this toolchain")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libpt_oracle_san.so")
+    subprocess.run(["make", "-C", os.path.join(root, "oracle"), "asan", f"SAN_OUT={so}", f"CXX={cxx}"], check=True, capture_output=True)
+    code = """
+import numpy as np
+from foundation_b200 import scenes
+from oracle.pt_oracle import OracleScene
+from tests.util import SMALL_SCENES, ray_mix
+from tests.test_oracle import degenerate_scene
+for make in (SMALL_SCENES['cornell'], SMALL_SCENES['instanced'], degenerate_scene):
+    sc = make(); o = OracleScene(sc)
+    lo, hi = scenes.scene_bounds(sc)
+    rays = ray_mix(sc, 256) if sc.view is not None else scenes.incoherent_rays(lo, hi, 1024, 3)
+    h, i = o.trace_closest(rays); b, _ = o.trace_closest(rays[:64], brute=True)
+    assert (h['prim'][:64] == b['prim']).all()
+    o.trace_any(rays)
+    o.blas(0)
+    if sc.view is not None:
+        o.render(16, 16, 3, 0, 2, 3, flags=48)
+print('sanitized run ok')
+"""
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1", PT_ORACLE_LIB=so, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=600)
+    assert r.returncode == 0 and "sanitized run ok" in r.stdout, r.stderr[-3000:]
+    assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
