@@ -119,6 +119,8 @@ struct foundation_pt_context {
 
     // committed scene
     bool committed = false, two_level = false, render_pending = false;
+    std::vector<cudaEvent_t> stage_events;            // FOUNDATION_PT_FLAG_STAGE_TIMING: pool of events, one per stage boundary
+    std::vector<int> stage_marks;                     // stage that ENDS at event i (-1 = start of the render)
     DevBuf d_nodes_all, d_tris_all, d_instances, d_inst_in, d_mesh_info, d_mats, d_lights;
     std::vector<PtMeshInfo> mesh_info;
     DevBuf d_tlas_order; uint32_t tlas_nodes = 0, num_inst = 0;
@@ -425,6 +427,17 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
     ss.sc.bg[0] = ctx->cfg.background[0]; ss.sc.bg[1] = ctx->cfg.background[1]; ss.sc.bg[2] = ctx->cfg.background[2];
     const bool sort = (ctx->cfg.flags & FOUNDATION_PT_FLAG_MATERIAL_SORT) && !(ctx->cfg.flags & FOUNDATION_PT_FLAG_NO_MATERIAL_SORT);
     uint32_t* status = ctx->d_status.as<uint32_t>();
+    // optional per-stage timing: one event per stage boundary, evaluated in foundation_pt_wait
+    const bool timing = (ctx->cfg.flags & FOUNDATION_PT_FLAG_STAGE_TIMING) != 0;
+    ctx->stage_marks.clear();
+    auto mark = [&](int stage) {
+        if (!timing) return;
+        const size_t i = ctx->stage_marks.size();
+        if (i >= ctx->stage_events.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; } ctx->stage_events.push_back(e); }
+        cudaEventRecord(ctx->stage_events[i], ctx->stream);
+        ctx->stage_marks.push_back(stage);
+    };
+    mark(-1);
     for (uint32_t smp = s0; smp < s0 + ns;) {
         const uint32_t batch = (s0 + ns - smp) < ctx->wave_samples ? (s0 + ns - smp) : ctx->wave_samples;
         const uint32_t S = ctx->num_slots * batch;
@@ -434,22 +447,28 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
         smp += batch;
         w.active = ctx->w_active.as<uint32_t>(); w.next = ctx->w_next.as<uint32_t>();
         PT_LAUNCH(ctx, k_raygen, g256, 256, w, f);
+        mark(0);
         for (uint32_t b = 0; b <= max_bounces; ++b) {
             if (sort) PT_LAUNCH(ctx, k_key_clear, 2, 1024, w.key_hist);
             PT_LAUNCH(ctx, k_extend<TWO>, gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
+            mark(1);
             const uint32_t* list = w.active;
             if (sort) {
                 PT_LAUNCH(ctx, k_key_hist, g256, 256, w);
                 PT_LAUNCH(ctx, k_key_scan, 1, 1024, w.key_hist);
                 PT_LAUNCH(ctx, k_key_scatter, g256, 256, w);
                 list = w.sorted;
+                mark(4);
             }
             PT_LAUNCH(ctx, k_shade<TWO>, g128, 128, ss, w, list);
+            mark(2);
             PT_LAUNCH(ctx, k_connect<TWO>, gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
             PT_LAUNCH(ctx, k_bounce_end, 1, 32, w);
+            mark(3);
             std::swap(w.active, w.next);
         }
         PT_LAUNCH(ctx, k_accumulate, grid_for(ctx, ctx->num_slots, 256, 8), 256, w, ctx->d_accum.as<float4>());
+        mark(5);
     }
     PT_CK(cudaGetLastError());
     return 0;
@@ -530,6 +549,7 @@ int32_t foundation_pt_destroy(foundation_pt_context* ctx) {
     if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2); if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
     cudaStream_t s1 = ctx->stream, s2 = ctx->stream2, s3 = ctx->stream3;
     delete ctx;   // frees device buffers
     if (s1) cudaStreamDestroy(s1); if (s2) cudaStreamDestroy(s2); if (s3) cudaStreamDestroy(s3);
@@ -825,6 +845,12 @@ int32_t foundation_pt_wait(foundation_pt_context* ctx) {
     PtWaveCounters c;
     PT_CK(cudaMemcpy(&c, ctx->w_ctr.p, sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.rays_extend = c.total_extend; ctx->stats.rays_shadow = c.total_shadow;
+    for (float& v : ctx->stats.stage_ms) v = 0.0f;
+    for (size_t i = 1; i < ctx->stage_marks.size(); ++i) {
+        float dt = 0.0f;
+        if (ctx->stage_marks[i] >= 0 && cudaEventElapsedTime(&dt, ctx->stage_events[i - 1], ctx->stage_events[i]) == cudaSuccess) ctx->stats.stage_ms[ctx->stage_marks[i]] += dt;
+    }
+    cudaGetLastError();
     return check_status(ctx);
     PT_CATCH(ctx)
 }

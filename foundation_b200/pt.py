@@ -17,7 +17,8 @@ from . import build as _build
 from .scenes import HIT_DTYPE, RAY_DTYPE, Scene  # noqa: F401
 
 OK, ERR_ARGUMENT, ERR_STATE, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-FLAG_NO_MATERIAL_SORT, FLAG_NO_NEE, FLAG_NO_BSDF_EMISSION, FLAG_MATERIAL_SORT, FLAG_SOBOL_JITTER, FLAG_SOBOL_PATH = 1, 2, 4, 8, 16, 32
+FLAG_NO_MATERIAL_SORT, FLAG_NO_NEE, FLAG_NO_BSDF_EMISSION, FLAG_MATERIAL_SORT, FLAG_SOBOL_JITTER, FLAG_SOBOL_PATH, FLAG_STAGE_TIMING = 1, 2, 4, 8, 16, 32, 64
+STAGE_NAMES = ("raygen", "extend", "shade", "connect", "material_sort", "accumulate")
 
 NODE_DTYPE = np.dtype([("p", "<f4", (3,)), ("e", "u1", (3,)), ("imask", "u1"), ("child_base", "<u4"), ("tri_base", "<u4"), ("meta", "u1", (8,)),
                        ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])
@@ -37,7 +38,8 @@ class BuildStats(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("kernel_launches", C.c_uint32), ("rays_extend", C.c_uint64), ("rays_shadow", C.c_uint64),
-                ("last_ms", C.c_float), ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("reserved", C.c_uint32), ("total_launches", C.c_uint64)]
+                ("last_ms", C.c_float), ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("reserved", C.c_uint32), ("total_launches", C.c_uint64),
+                ("stage_ms", C.c_float * 6)]
 
 
 # every symbol include/foundation_pt.h declares (tests check the library exports exactly these)

@@ -75,6 +75,7 @@ enum {
     FOUNDATION_PT_FLAG_NO_NEE = 1u << 1,           /* BSDF sampling only (oracle self-checks)                  */
     FOUNDATION_PT_FLAG_NO_BSDF_EMISSION = 1u << 2, /* NEE only: emitters hit by BSDF rays after bounce 0 add nothing */
     FOUNDATION_PT_FLAG_SOBOL_JITTER = 1u << 4,     /* sub-pixel positions from a per-pixel scrambled Sobol (0,2)-sequence instead of PCG32 */
+    FOUNDATION_PT_FLAG_STAGE_TIMING = 1u << 6,     /* record CUDA events between the wavefront stages of a render -> foundation_pt_stats.stage_ms */
     FOUNDATION_PT_FLAG_SOBOL_PATH = 1u << 5,       /* light-point and BSDF-direction samples of every path vertex from padded, Owen-scrambled (0,2)-sequences */
     FOUNDATION_PT_FLAG_MATERIAL_SORT = 1u << 3     /* counting-sort live paths by material id before shading.  Off by default: with ONE
                                                       surface model for all materials the sort costs 8-14 % of a pass and buys nothing
@@ -134,6 +135,9 @@ typedef struct foundation_pt_stats {
     float shade_ms;            /* reserved (0): per-stage times of a render are taken with ncu, see profiles/               */
     uint32_t reserved;
     uint64_t total_launches;   /* since create */
+    float stage_ms[6];         /* FOUNDATION_PT_FLAG_STAGE_TIMING: device time of the last render per wavefront stage (CUDA events between the
+                                  launches): [0] ray generation, [1] extend (closest hit), [2] shade + NEE, [3] connect (any hit),
+                                  [4] material sort, [5] accumulate.  All 0 without the flag.                                      */
 } foundation_pt_stats;
 
 /* ---- lifetime (reference slot: Renderer::Renderer / ~Renderer, src/Renderer/Renderer.cpp:34-311, 402-406) ---- */

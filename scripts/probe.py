@@ -62,3 +62,5 @@ if a.spp:
     st = tr.stats()
     print(f"render {a.spp} spp: {st.last_ms:.1f} ms -> {a.spp / st.last_ms * 1e3:.2f} spp/s; rays ext {st.rays_extend} shadow {st.rays_shadow} -> "
           f"{(st.rays_extend + st.rays_shadow) / st.last_ms / 1e3:.1f} Mrays/s; launches {st.kernel_launches}", flush=True)
+    if a.flags & pt.FLAG_STAGE_TIMING:
+        print("stages (ms): " + ", ".join(f"{n} {v:.2f}" for n, v in zip(pt.STAGE_NAMES, st.stage_ms)), flush=True)

@@ -427,3 +427,19 @@ def test_render_async_plus_wait_equals_render(gpu):
     assert np.array_equal(img, a.read_accum())
     b.wait()                                 # nothing in flight: a no-op
     a.close(); b.close()
+
+
+def test_stage_timing_flag_reports_where_a_render_spends_its_time(gpu):
+    """FOUNDATION_PT_FLAG_STAGE_TIMING (CUDA events around each wavefront stage): the per-stage times add up to the
+    call's device time, the frame is unchanged, and without the flag the array stays zero."""
+    sc = SMALL_SCENES["terrain"]()
+    a = pt.PathTracer(sc.width, sc.height, seed=2, background=sc.background); a.load(sc)
+    b = pt.PathTracer(sc.width, sc.height, seed=2, background=sc.background, flags=pt.FLAG_STAGE_TIMING); b.load(sc)
+    a.render(0, 8, 4); b.render(0, 8, 4)
+    assert np.array_equal(a.read_accum(), b.read_accum())
+    sa, sb = a.stats(), b.stats()
+    assert all(v == 0.0 for v in sa.stage_ms)
+    st = dict(zip(pt.STAGE_NAMES, sb.stage_ms))
+    assert st["extend"] > 0 and st["shade"] > 0 and st["connect"] > 0 and st["raygen"] > 0 and st["accumulate"] > 0 and st["material_sort"] == 0.0
+    assert 0.7 * sb.last_ms <= sum(sb.stage_ms) <= 1.02 * sb.last_ms, (sb.last_ms, st)
+    a.close(); b.close()
