@@ -14,6 +14,9 @@
 #include <vector>
 
 #include "../../include/foundation_pt.h"
+#ifndef PT_AGGLOMERATIVE
+#define PT_AGGLOMERATIVE 1   // 1: the radix tree is built bottom-up inside the refit (k_refit_agg, k_refit_agg_up); 0: k_karras + k_refit + k_refit_up
+#endif
 #include "pt_kernels.cuh"
 
 static_assert(sizeof(foundation_pt_ray) == 32 && sizeof(foundation_pt_hit) == 16, "ABI record sizes");
@@ -230,19 +233,35 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
     size_t ni = n > 1 ? n - 1 : 1;
     PT_CK(cost.alloc(ni * 32)); PT_CK(plan.alloc(ni * 8));
     PT_CK(left.alloc(ni * 4)); PT_CK(right.alloc(ni * 4)); PT_CK(first.alloc(ni * 4)); PT_CK(last.alloc(ni * 4));
-    PT_CK(parent.alloc((2 * (size_t)n) * 4)); PT_CK(box.alloc((2 * (size_t)n) * sizeof(PtBox))); PT_CK(flags.alloc(ni * 4));
+#if !PT_AGGLOMERATIVE
+    PT_CK(parent.alloc((2 * (size_t)n) * 4));
+#endif
+    PT_CK(box.alloc((2 * (size_t)n) * sizeof(PtBox))); PT_CK(flags.alloc(ni * 4));
     PT_CK(cudaMemsetAsync(flags.p, 0, ni * 4, ctx->stream));
     PtBvh2 b; b.n = n; b.left = left.as<uint32_t>(); b.right = right.as<uint32_t>(); b.first = first.as<uint32_t>(); b.last = last.as<uint32_t>();
     b.parent = parent.as<uint32_t>(); b.box = box.as<PtBox>(); b.cost = cost.as<float>(); b.plan = plan.as<uint64_t>();
+#if !PT_AGGLOMERATIVE
     if (n > 1) PT_LAUNCH(ctx, k_karras, grid_for(ctx, n - 1, 256, 8), 256, keys.as<uint64_t>(), b);
-    {   // A4: tile-local part (shared memory, round-synchronous), then the few subtree roots per tile climb the upper levels
+#endif
+    DevBuf root_ref;                 // BVH2 ref of the root: 0 with Karras' numbering, the top split with the agglomerative build
+    PT_CK(root_ref.alloc(16));
+    PT_CK(cudaMemsetAsync(root_ref.p, 0, 16, ctx->stream));
+    {   // A4 (+ A3 when agglomerative): tile-local part (shared memory, round-synchronous), then the few subtree roots per tile climb the upper levels
         DevBuf up_list, up_count;   // freed stream-ordered when the scope ends
         PT_CK(up_list.alloc((size_t)n * 4)); PT_CK(up_count.alloc(16));
         PT_CK(cudaMemsetAsync(up_count.p, 0, 4, ctx->stream));
         static int refit_blocks = 0;     // resident blocks per SM (shared-memory bound): the grid is exactly one wave, tiles are strided over it
+#if PT_AGGLOMERATIVE
+        if (!refit_blocks && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&refit_blocks, k_refit_agg, PT_REFIT_TILE, 0) != cudaSuccess || refit_blocks < 1)) { cudaGetLastError(); refit_blocks = 4; }
+        PT_LAUNCH(ctx, k_refit_agg, grid_for(ctx, n, PT_REFIT_TILE, (uint32_t)refit_blocks), PT_REFIT_TILE, b, keys.as<uint64_t>(), d_prim_box, vals.as<uint32_t>(),
+                  up_list.as<uint32_t>(), up_count.as<uint32_t>(), root_ref.as<uint32_t>(), max_leaf);
+        if (n > 1) PT_LAUNCH(ctx, k_refit_agg_up, grid_for(ctx, n / 16 + 1, 128, 8), 128, b, keys.as<uint64_t>(), up_list.as<uint32_t>(), up_count.as<uint32_t>(),
+                             flags.as<uint32_t>(), root_ref.as<uint32_t>(), max_leaf);
+#else
         if (!refit_blocks && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&refit_blocks, k_refit, PT_REFIT_TILE, 0) != cudaSuccess || refit_blocks < 1)) { cudaGetLastError(); refit_blocks = 4; }
         PT_LAUNCH(ctx, k_refit, grid_for(ctx, n, PT_REFIT_TILE, (uint32_t)refit_blocks), PT_REFIT_TILE, b, d_prim_box, vals.as<uint32_t>(), up_list.as<uint32_t>(), up_count.as<uint32_t>(), max_leaf);
         if (n > 1) PT_LAUNCH(ctx, k_refit_up, grid_for(ctx, n / 16 + 1, 128, 8), 128, b, up_list.as<uint32_t>(), up_count.as<uint32_t>(), flags.as<uint32_t>(), max_leaf);
+#endif
     }
     // collapse, level by level
     DevBuf nodes_tmp, refs_a, refs_b, slots, n_int, n_prim, totals;
@@ -250,8 +269,7 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
     PT_CK(refs_a.alloc((size_t)n * 4)); PT_CK(refs_b.alloc((size_t)n * 4));
     PT_CK(out->leaf_seq.alloc((size_t)n * 4));
     PT_CK(totals.alloc(16));
-    uint32_t zero = 0;
-    PT_CK(cudaMemcpyAsync(refs_a.p, &zero, 4, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaMemcpyAsync(refs_a.p, root_ref.p, 4, cudaMemcpyDeviceToDevice, ctx->stream));
     uint32_t m = 1, level_start = 0, prim_total = 0;
     {   // top of the tree: all levels of at most PT_TOP_NODES wide nodes in one single-block launch
         PT_LAUNCH(ctx, k_collapse_top, 1, PT_TOP_NODES, b, refs_a.as<uint32_t>(), refs_b.as<uint32_t>(), max_leaf, d_bp, nodes_tmp.as<PtNode8>(), out->leaf_seq.as<uint32_t>(),

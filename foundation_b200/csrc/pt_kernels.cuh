@@ -477,6 +477,174 @@ __global__ void __launch_bounds__(128) k_refit_up(PtBvh2 b, const uint32_t* up_l
 }
 
 // ---------------------------------------------------------------------------------------------------
+// A3 + A4 fused (PT_AGGLOMERATIVE): the radix tree is built bottom-up WHILE the refit climbs (Apetrei, "Fast and Simple Agglomerative
+// LBVH Construction", 2014).  A finished subtree over sorted leaves [l, r] joins the neighbour it shares the longer key prefix with:
+// delta(r, r+1) > delta(l-1, l)  ->  it is the LEFT child of node r, else the RIGHT child of node l-1 (a node's id is the position of
+// its split).  Same tree as Karras' top-down emit (the deltas are all distinct thanks to the index tie-break), different node ids —
+// nothing downstream depends on the ids — and no binary searches: k_karras (divergence-bound, 0.43 ms for 10 M keys) and the
+// parent / left / right / first / last round trip through HBM disappear.  Tile-local test without knowing the sibling: the parent of a
+// left child [l, r] is local iff the right sibling, which starts at r+1 and ends before the first key that does NOT share more than
+// delta(r, r+1) bits with key r+1, ends inside the tile: one more delta against the key just past the tile (mirrored for right children).
+// Both children evaluate the same predicate, so they meet either in shared memory or through the global protocol, never one in each.
+struct PtJoin { uint32_t p; bool left; int q; };
+__device__ __forceinline__ PtJoin pt_join(const uint64_t* k, uint32_t koff, uint32_t n, uint32_t l, uint32_t r) {   // k[i - koff] = key of sorted position i
+    const int dl = l > 0 ? pt_delta(k[l - 1 - koff], k[l - koff], l - 1, l) : -1;
+    const int dr = r + 1 < n ? pt_delta(k[r - koff], k[r + 1 - koff], r, r + 1) : -1;
+    PtJoin j; j.left = dr > dl; j.p = j.left ? r : l - 1; j.q = j.left ? dr : dl;
+    return j;
+}
+__global__ void __launch_bounds__(PT_REFIT_TILE) k_refit_agg(PtBvh2 b, const uint64_t* keys, const PtBox* prim_box, const uint32_t* order, uint32_t* up_list,
+                                                            uint32_t* up_count, uint32_t* root_out, uint32_t max_leaf) {
+    constexpr uint32_t T = PT_REFIT_TILE;
+    __shared__ PtBox s_box[2 * T];
+    __shared__ float4 s_cost[T][2];
+    __shared__ unsigned long long s_plan[T];
+    __shared__ uint64_t s_key[T + 2];                    // keys of positions tile_lo - 1 .. tile_hi + 1
+    __shared__ uint32_t s_left[T], s_right[T], s_first[T], s_last[T];
+    __shared__ uint32_t s_flag[T];
+    __shared__ uint32_t s_q[3][T / 2];
+    __shared__ uint32_t s_up[T];
+    __shared__ uint32_t s_qn[3], s_upn;
+    const uint32_t n = b.n, tid = threadIdx.x;
+    if (n == 1) { if (pt_gtid() == 0) b.box[0] = prim_box[order[0]]; return; }
+    for (uint32_t tile_lo = blockIdx.x * T; tile_lo < n; tile_lo += gridDim.x * T) {
+        const uint32_t tile_hi = min(n, tile_lo + T) - 1u;
+        const uint32_t j = tile_lo + tid;
+        const uint32_t koff = tile_lo - 1u;              // s_key[i - koff]; position tile_lo - 1 only exists when tile_lo > 0 (never read otherwise)
+        if (j < n) {
+            const PtBox lb = prim_box[order[j]];
+            s_box[T + tid] = lb;
+            b.box[n - 1 + j] = lb;
+            s_key[tid + 1] = keys[j];
+        }
+        if (tid == 0 && tile_lo > 0) s_key[0] = keys[tile_lo - 1];
+        if (tid == 0 && tile_hi + 1 < n) s_key[tile_hi + 2 - tile_lo] = keys[tile_hi + 1];
+        s_flag[tid] = 0;
+        if (tid == 0) { s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0; s_upn = 0; }
+        __syncthreads();
+        // subtree `ref` over [l, r] (inside the tile) is finished: find its parent, hand it over
+        auto deliver = [&](uint32_t ref, uint32_t l, uint32_t r, uint32_t q) {
+            if (l == 0 && r == n - 1) { *root_out = ref; return; }                      // the whole tree fits one tile
+            const PtJoin jn = pt_join(s_key, koff, n, l, r);
+            bool local;
+            if (jn.left) local = r < tile_hi && (tile_hi + 1 >= n || pt_delta(s_key[r + 1 - koff], s_key[tile_hi + 1 - koff], r + 1, tile_hi + 1) <= jn.q);
+            else local = l > tile_lo && (tile_lo == 0 || pt_delta(s_key[tile_lo - 1 - koff], s_key[l - 1 - koff], tile_lo - 1, l - 1) <= jn.q);
+            if (!local) { s_up[atomicAdd(&s_upn, 1u)] = ref; return; }
+            const uint32_t lp = jn.p - tile_lo;
+            if (jn.left) { s_left[lp] = ref; s_first[lp] = l; } else { s_right[lp] = ref; s_last[lp] = r; }
+            __threadfence_block();
+            if (atomicAdd(&s_flag[lp], 1u) == 1u) s_q[q][atomicAdd(&s_qn[q], 1u)] = jn.p;
+        };
+        if (j < n) deliver(n - 1 + j, j, j, 0u);
+        __syncthreads();
+        for (uint32_t cur = 0;; cur = cur == 2u ? 0u : cur + 1u) {
+            const uint32_t cnt = s_qn[cur], nxt = cur == 2u ? 0u : cur + 1u;
+            if (cnt == 0) break;
+            if (tid == 0) s_qn[nxt == 2u ? 0u : nxt + 1u] = 0;
+            if (tid < cnt) {
+                const uint32_t p = s_q[cur][tid], lp = p - tile_lo;
+                const uint32_t L = *const_cast<volatile uint32_t*>(&s_left[lp]), R = *const_cast<volatile uint32_t*>(&s_right[lp]);
+                const uint32_t f = *const_cast<volatile uint32_t*>(&s_first[lp]), la = *const_cast<volatile uint32_t*>(&s_last[lp]);
+                float cl[7], cr[7], mc[7];
+                PtBox bl, br;
+                if (L >= n - 1) {
+                    bl = pt_lds_box(&s_box[T + (L - (n - 1)) - tile_lo]);
+                    const float lc = pt_plan_leaf_cost(bl);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) cl[i] = lc;
+                } else {
+                    bl = pt_lds_box(&s_box[L - tile_lo]);
+                    const volatile float* c = reinterpret_cast<const volatile float*>(&s_cost[L - tile_lo][0]);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) cl[i] = c[i];
+                }
+                if (R >= n - 1) {
+                    br = pt_lds_box(&s_box[T + (R - (n - 1)) - tile_lo]);
+                    const float lc = pt_plan_leaf_cost(br);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) cr[i] = lc;
+                } else {
+                    br = pt_lds_box(&s_box[R - tile_lo]);
+                    const volatile float* c = reinterpret_cast<const volatile float*>(&s_cost[R - tile_lo][0]);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) cr[i] = c[i];
+                }
+                pt_box_union(bl, br);
+                s_box[lp] = bl;
+                s_plan[lp] = pt_plan_node(cl, cr, pt_box_area(bl.lox, bl.loy, bl.loz, bl.hix, bl.hiy, bl.hiz), la - f + 1u, max_leaf, mc);
+                s_cost[lp][0] = make_float4(mc[0], mc[1], mc[2], mc[3]); s_cost[lp][1] = make_float4(mc[4], mc[5], mc[6], 0.0f);
+                deliver(p, f, la, nxt);
+            }
+            __syncthreads();
+        }
+        // write back the nodes finished in this tile: boxes, costs, plan AND their topology (the collapse reads left / right / first / last)
+        if (j < n - 1 && s_flag[tid] == 2u) {
+            b.box[j] = s_box[tid];
+            float4* dst = reinterpret_cast<float4*>(b.cost + 8 * (size_t)j);
+            dst[0] = s_cost[tid][0]; dst[1] = s_cost[tid][1];
+            b.plan[j] = s_plan[tid];
+            b.left[j] = s_left[tid]; b.right[j] = s_right[tid]; b.first[j] = s_first[tid]; b.last[j] = s_last[tid];
+        }
+        __syncthreads();
+        if (tid == 0) s_qn[0] = atomicAdd(up_count, s_upn);
+        __syncthreads();
+        if (tid < s_upn) up_list[s_qn[0] + tid] = s_up[tid];
+        __syncthreads();
+    }
+}
+// Upper levels: the roots of the tile-local subtrees keep joining neighbours through global memory.  The first child to arrive leaves
+// its link and its end of the range in the parent's record; the second one reads them back (L2), owns the parent and climbs on.
+__global__ void __launch_bounds__(128) k_refit_agg_up(PtBvh2 b, const uint64_t* keys, const uint32_t* up_list, const uint32_t* up_count, uint32_t* flags,
+                                                      uint32_t* root_out, uint32_t max_leaf) {
+    const uint32_t n = b.n, m = *up_count;
+    for (uint32_t k = pt_gtid(); k < m; k += pt_gsize()) {
+        uint32_t me = up_list[k];
+        uint32_t l, r;
+        PtBox mine = b.box[me];
+        float mc[7];
+        if (me >= n - 1) {
+            l = r = me - (n - 1);
+            const float lc = pt_plan_leaf_cost(mine);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) mc[i] = lc;
+        } else {
+            l = b.first[me]; r = b.last[me];
+            const float4 c0 = *reinterpret_cast<const float4*>(b.cost + 8 * (size_t)me), c1 = *reinterpret_cast<const float4*>(b.cost + 8 * (size_t)me + 4);
+            mc[0] = c0.x; mc[1] = c0.y; mc[2] = c0.z; mc[3] = c0.w; mc[4] = c1.x; mc[5] = c1.y; mc[6] = c1.z;
+        }
+        for (;;) {
+            if (l == 0 && r == n - 1) { *root_out = me; break; }
+            const PtJoin jn = pt_join(keys, 0u, n, l, r);
+            const uint32_t cur = jn.p;
+            if (jn.left) { b.left[cur] = me; b.first[cur] = l; } else { b.right[cur] = me; b.last[cur] = r; }
+            __threadfence();                       // publish box / cost of `me` and its link in `cur` before announcing arrival
+            if (atomicAdd(&flags[cur], 1u) == 0u) break;
+            uint32_t sib;
+            if (jn.left) { sib = __ldcg(&b.right[cur]); r = __ldcg(&b.last[cur]); } else { sib = __ldcg(&b.left[cur]); l = __ldcg(&b.first[cur]); }
+            const PtBox s = pt_ldcg_box(&b.box[sib]);
+            float sc[7];
+            if (sib >= n - 1) {
+                const float lc = pt_plan_leaf_cost(s);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) sc[i] = lc;
+            } else {
+                const float4 c0 = __ldcg(reinterpret_cast<const float4*>(b.cost + 8 * (size_t)sib)), c1 = __ldcg(reinterpret_cast<const float4*>(b.cost + 8 * (size_t)sib + 4));
+                sc[0] = c0.x; sc[1] = c0.y; sc[2] = c0.z; sc[3] = c0.w; sc[4] = c1.x; sc[5] = c1.y; sc[6] = c1.z;
+            }
+            pt_box_union(mine, s);
+            b.box[cur] = mine;
+            float cl[7], cr[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { cl[i] = jn.left ? mc[i] : sc[i]; cr[i] = jn.left ? sc[i] : mc[i]; }
+            b.plan[cur] = pt_plan_node(cl, cr, pt_box_area(mine.lox, mine.loy, mine.loz, mine.hix, mine.hiy, mine.hiz), r - l + 1u, max_leaf, mc);
+            float4* dst = reinterpret_cast<float4*>(b.cost + 8 * (size_t)cur);
+            dst[0] = make_float4(mc[0], mc[1], mc[2], mc[3]); dst[1] = make_float4(mc[4], mc[5], mc[6], 0.0f);
+            me = cur;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // A5: level-synchronous BVH2 -> BVH8 collapse
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_collapse_select(PtBvh2 b, const uint32_t* refs, uint32_t m, uint32_t max_leaf, uint32_t* slots, uint32_t* n_int,
