@@ -58,6 +58,25 @@ PT_HD void pt_karras_node(uint32_t idx, const uint64_t* keys, const PtBvh2& b) {
     b.parent[L] = idx; b.parent[R] = idx;
 }
 
+// ---- A3, bottom-up form (Apetrei 2014): where does a finished subtree go? -------------------------------
+// A subtree over sorted leaves [l, r] joins the neighbour it shares the longer key prefix with: delta(r, r+1) > delta(l-1, l) -> it
+// is the LEFT child of node r, else the RIGHT child of node l-1 (node id = position of its split).  k[i - koff] is the key of sorted
+// position i (koff lets a kernel pass a shared-memory window of the key array).  This yields exactly the tree of pt_karras_node.
+struct PtJoin { uint32_t p; bool left; int q; };   // parent id, which child we are, the parent's common-prefix length
+PT_HD PtJoin pt_join(const uint64_t* k, uint32_t koff, uint32_t n, uint32_t l, uint32_t r) {
+    const int dl = l > 0 ? pt_delta(k[l - 1 - koff], k[l - koff], l - 1, l) : -1;
+    const int dr = r + 1 < n ? pt_delta(k[r - koff], k[r + 1 - koff], r, r + 1) : -1;
+    PtJoin j; j.left = dr > dl; j.p = j.left ? r : l - 1; j.q = j.left ? dr : dl;
+    return j;
+}
+// Does the parent's whole leaf range lie inside [tile_lo, tile_hi]?  Decided from this child's side only: the sibling of a left child
+// starts at r+1 and ends before the first key that does not share more than q bits with key r+1 (keys are sorted, so one delta against
+// the key just past the tile answers it); mirrored for a right child.  Both children of a node compute the same answer.
+PT_HD bool pt_join_is_local(const uint64_t* k, uint32_t koff, uint32_t n, uint32_t l, uint32_t r, const PtJoin& jn, uint32_t tile_lo, uint32_t tile_hi) {
+    if (jn.left) return r < tile_hi && (tile_hi + 1 >= n || pt_delta(k[r + 1 - koff], k[tile_hi + 1 - koff], r + 1, tile_hi + 1) <= jn.q);
+    return l > tile_lo && (tile_lo == 0 || pt_delta(k[tile_lo - 1 - koff], k[l - 1 - koff], tile_lo - 1, l - 1) <= jn.q);
+}
+
 // ---- A5 phase 0: the collapse plan --------------------------------------------------------------------
 // Which descendants of a BVH2 node become the (at most 8) children of its wide node is decided by the surface-area-cost dynamic
 // programme of Ylitie, Karras, Laine, "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017), section 3.1:

@@ -486,13 +486,6 @@ __global__ void __launch_bounds__(128) k_refit_up(PtBvh2 b, const uint32_t* up_l
 // left child [l, r] is local iff the right sibling, which starts at r+1 and ends before the first key that does NOT share more than
 // delta(r, r+1) bits with key r+1, ends inside the tile: one more delta against the key just past the tile (mirrored for right children).
 // Both children evaluate the same predicate, so they meet either in shared memory or through the global protocol, never one in each.
-struct PtJoin { uint32_t p; bool left; int q; };
-__device__ __forceinline__ PtJoin pt_join(const uint64_t* k, uint32_t koff, uint32_t n, uint32_t l, uint32_t r) {   // k[i - koff] = key of sorted position i
-    const int dl = l > 0 ? pt_delta(k[l - 1 - koff], k[l - koff], l - 1, l) : -1;
-    const int dr = r + 1 < n ? pt_delta(k[r - koff], k[r + 1 - koff], r, r + 1) : -1;
-    PtJoin j; j.left = dr > dl; j.p = j.left ? r : l - 1; j.q = j.left ? dr : dl;
-    return j;
-}
 __global__ void __launch_bounds__(PT_REFIT_TILE) k_refit_agg(PtBvh2 b, const uint64_t* keys, const PtBox* prim_box, const uint32_t* order, uint32_t* up_list,
                                                             uint32_t* up_count, uint32_t* root_out, uint32_t max_leaf) {
     constexpr uint32_t T = PT_REFIT_TILE;
@@ -526,9 +519,7 @@ __global__ void __launch_bounds__(PT_REFIT_TILE) k_refit_agg(PtBvh2 b, const uin
         auto deliver = [&](uint32_t ref, uint32_t l, uint32_t r, uint32_t q) {
             if (l == 0 && r == n - 1) { *root_out = ref; return; }                      // the whole tree fits one tile
             const PtJoin jn = pt_join(s_key, koff, n, l, r);
-            bool local;
-            if (jn.left) local = r < tile_hi && (tile_hi + 1 >= n || pt_delta(s_key[r + 1 - koff], s_key[tile_hi + 1 - koff], r + 1, tile_hi + 1) <= jn.q);
-            else local = l > tile_lo && (tile_lo == 0 || pt_delta(s_key[tile_lo - 1 - koff], s_key[l - 1 - koff], tile_lo - 1, l - 1) <= jn.q);
+            const bool local = pt_join_is_local(s_key, koff, n, l, r, jn, tile_lo, tile_hi);
             if (!local) { s_up[atomicAdd(&s_upn, 1u)] = ref; return; }
             const uint32_t lp = jn.p - tile_lo;
             if (jn.left) { s_left[lp] = ref; s_first[lp] = l; } else { s_right[lp] = ref; s_last[lp] = r; }

@@ -135,6 +135,7 @@ def _emu():
     subprocess.run(["make", "-C", os.path.join(HERE, "emu")], check=True, capture_output=True)
     E = C.CDLL(so)
     E.emu_build.restype = C.c_uint32
+    E.emu_build_agglomerative.restype = C.c_uint32
     return E
 
 
@@ -164,6 +165,12 @@ def _check_product_bodies(name, sc, o, E, leaf):
         on, ot, oo = o.blas(mid)
         assert nn == len(on) and nodes[:nn].tobytes() == on.tobytes(), f"{name} mesh {mid}: nodes differ"
         assert np.array_equal(order, oo) and np.array_equal(ot["prim"], order[seq])
+        # the product's default build: bottom-up agglomerative joins (pt_join / pt_join_is_local), emulated tile by tile like the kernels,
+        # for several tile sizes (tiny tiles push almost every node through the "global" path, one big tile keeps everything local)
+        for tile in (2, 5, 64, 256, 1 << 30):
+            n2 = np.zeros(n + 1, NODE_DTYPE); s2 = np.zeros(n, np.uint32); o2 = np.zeros(n, np.uint32)
+            m2 = E.emu_build_agglomerative(_p(box), _p(cent), C.c_uint32(n), C.c_uint32(leaf), _p(lo), _p(hi), _p(n2), _p(s2), _p(o2), C.c_uint32(tile))
+            assert m2 == nn and n2[:m2].tobytes() == on.tobytes() and np.array_equal(s2, seq) and np.array_equal(o2, order), f"{name} mesh {mid}: agglomerative build, tile {tile}"
         flat_nodes.append(on); flat_tris.append(ot)
     rays = ray_mix(sc, 2048)
     if sc.instances is None:
@@ -323,6 +330,34 @@ def test_degenerate_and_duplicate_triangles():
     assert (area > 0).all() and len(hit) > 100
     dup_hit = hit[(hit >= 100) & (hit < 110)]
     assert len(dup_hit) == 0, "a duplicated triangle must lose the tie to its lower-index twin"
+
+
+def test_product_bodies_on_degenerate_and_chain_like_inputs():
+    """Equal Morton keys (duplicated / coincident triangles: the radix tree is decided by the index tie-break) through the emulated product
+    build, Karras and agglomerative, at several tile sizes."""
+    E = _emu()
+    rng = np.random.default_rng(5)
+    tri = np.asarray([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    pos = np.concatenate([np.tile(tri, (300, 1)), (rng.uniform(-50, 50, (7, 1, 3)) + tri[None]).reshape(-1, 3).astype(np.float32)])
+    idx = np.arange(pos.shape[0], dtype=np.uint32).reshape(-1, 3)
+    chain = scenes.Scene("chain", [scenes.Mesh(np.ascontiguousarray(pos), idx, np.zeros(idx.shape[0], np.uint32))], np.asarray([[.8, .8, .8, .5, 0, 0, 0, 0]], np.float32))
+    for sc in (degenerate_scene(), chain):
+        sc.view = None
+        o = OracleScene(sc)
+        for mid, mesh in enumerate(sc.meshes):
+            v = mesh.positions[mesh.indices].astype(np.float32)
+            box = np.ascontiguousarray(np.concatenate([v.min(1), v.max(1)], 1), np.float32)
+            cent = np.ascontiguousarray(((v[:, 0] + v[:, 1]) + v[:, 2]) * np.float32(0.333333343267440796), np.float32)
+            n = len(v)
+            on, ot, oo = o.blas(mid)
+            lo = np.zeros(3, np.float32); hi = np.zeros(3, np.float32)
+            for tile in (0, 3, 64, 256):
+                nodes = np.zeros(n + 1, NODE_DTYPE); seq = np.zeros(n, np.uint32); order = np.zeros(n, np.uint32)
+                if tile == 0:
+                    nn = E.emu_build(_p(box), _p(cent), C.c_uint32(n), C.c_uint32(1), _p(lo), _p(hi), _p(nodes), _p(seq), _p(order))
+                else:
+                    nn = E.emu_build_agglomerative(_p(box), _p(cent), C.c_uint32(n), C.c_uint32(1), _p(lo), _p(hi), _p(nodes), _p(seq), _p(order), C.c_uint32(tile))
+                assert nn == len(on) and nodes[:nn].tobytes() == on.tobytes() and np.array_equal(order, oo), (sc.name, tile)
 
 
 def test_bsdf_matches_independent_float64_formula():
