@@ -576,6 +576,7 @@ int32_t foundation_pt_destroy(foundation_pt_context* ctx) {
 
 int32_t foundation_pt_materials_set(foundation_pt_context* ctx, const foundation_pt_material* materials, uint32_t count) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (!materials || count == 0) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "materials NULL or empty");
     PT_TRY
     ctx->mats.resize(count);
@@ -588,6 +589,7 @@ int32_t foundation_pt_materials_set(foundation_pt_context* ctx, const foundation
 int32_t foundation_pt_mesh_create(foundation_pt_context* ctx, const void* positions, size_t pos_stride_bytes, uint32_t num_vertices, const void* indices,
                                   uint32_t index_format, uint32_t num_triangles, const uint32_t* material_ids, uint32_t* out_mesh_id) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (!positions || num_vertices == 0 || num_triangles == 0) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_create: empty mesh");
     if (pos_stride_bytes < 12 || (pos_stride_bytes & 3) || pos_stride_bytes > 4096) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_create: stride must be a multiple of 4, >= 12");
     if (index_format != FOUNDATION_PT_INDEX_U16 && index_format != FOUNDATION_PT_INDEX_U32 && index_format != FOUNDATION_PT_INDEX_NONE)
@@ -625,6 +627,7 @@ int32_t foundation_pt_mesh_create(foundation_pt_context* ctx, const void* positi
 
 int32_t foundation_pt_instances_set(foundation_pt_context* ctx, const foundation_pt_instance* instances, uint32_t count) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (!instances || count == 0) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "instances NULL or empty");
     PT_TRY
     for (uint32_t i = 0; i < count; ++i)      // singular transforms are detected on the device at scene_commit (ERR_ARGUMENT there)
@@ -637,6 +640,7 @@ int32_t foundation_pt_instances_set(foundation_pt_context* ctx, const foundation
 
 int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_build_stats* stats) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (ctx->meshes.empty()) return ctx->fail(FOUNDATION_PT_ERR_STATE, "scene_commit: no meshes");
     if (stats && stats->struct_size != sizeof(foundation_pt_build_stats)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "build_stats struct_size mismatch");
     PT_TRY
@@ -811,6 +815,7 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
 
 int32_t foundation_pt_camera_set(foundation_pt_context* ctx, const float view[16], const float proj[16]) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (!view || !proj) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "camera_set: NULL matrix");
     if (!pt_camera_derive(view, proj, &ctx->cam)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "camera_set: singular view/projection");
     ctx->cam_set = true;
@@ -934,6 +939,7 @@ int32_t foundation_pt_accum_device_ptr(foundation_pt_context* ctx, void** out_de
 // ---- explicit ray sets --------------------------------------------------------------------------------
 int32_t foundation_pt_rays_upload(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (!rays && count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "rays_upload: NULL rays");
     PT_TRY
     cudaSetDevice(ctx->device);
@@ -981,6 +987,7 @@ int32_t foundation_pt_rays_trace_brute(foundation_pt_context* ctx, uint64_t firs
 
 int32_t foundation_pt_rays_download_hits(foundation_pt_context* ctx, uint64_t first, uint64_t count, foundation_pt_hit* out_hits, uint32_t* out_inst) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (first + count > ctx->num_rays) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "download_hits: range exceeds the uploaded ray set");
     cudaSetDevice(ctx->device);
     if (out_hits && count) PT_CK(cudaMemcpyAsync(out_hits, ctx->d_hits.as<float4>() + first, count * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1038,6 +1045,7 @@ int32_t foundation_pt_trace_any(foundation_pt_context* ctx, const foundation_pt_
 
 int32_t foundation_pt_stats_get(foundation_pt_context* ctx, foundation_pt_stats* stats) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (!stats || stats->struct_size != sizeof(foundation_pt_stats)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "stats_get: NULL or struct_size mismatch");
     ctx->stats.struct_size = sizeof(foundation_pt_stats);
     ctx->stats.total_launches = ctx->total_launches;
@@ -1048,6 +1056,7 @@ int32_t foundation_pt_stats_get(foundation_pt_context* ctx, foundation_pt_stats*
 int32_t foundation_pt_blas_download(foundation_pt_context* ctx, uint32_t mesh_id, void* nodes, size_t nodes_bytes, void* tris, size_t tris_bytes, uint32_t* order,
                                     size_t order_bytes, uint64_t* out_num_nodes, uint64_t* out_num_tris) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (mesh_id >= ctx->meshes.size()) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "blas_download: mesh_id out of range");
     Mesh& m = ctx->meshes[mesh_id];
     if (!m.d_nodes.p) return ctx->fail(FOUNDATION_PT_ERR_STATE, "blas_download: scene not committed");
@@ -1063,6 +1072,7 @@ int32_t foundation_pt_blas_download(foundation_pt_context* ctx, uint32_t mesh_id
 int32_t foundation_pt_tlas_download(foundation_pt_context* ctx, void* nodes, size_t nodes_bytes, uint32_t* order, size_t order_bytes, uint64_t* out_num_nodes,
                                     uint64_t* out_num_instances) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
     if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "tlas_download: scene not committed");
     cudaSetDevice(ctx->device);
     if (out_num_nodes) *out_num_nodes = ctx->tlas_nodes;
