@@ -511,3 +511,38 @@ print('sanitized run ok')
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=600)
     assert r.returncode == 0 and "sanitized run ok" in r.stdout, r.stderr[-3000:]
     assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
+
+
+def test_randomised_meshes_through_both_emulated_builds():
+    """120 random triangle soups — uniform, snapped to a coarse grid (many equal Morton keys), duplicated triangles, extreme aspect ratio —
+    with 1 .. 2000 triangles, both leaf sizes: the emulated Karras build and the emulated agglomerative build at tile sizes 2, 7, 64, 256
+    reproduce the oracle's BVH8 byte for byte."""
+    E = _emu()
+    rng = np.random.default_rng(123)
+    for trial in range(120):
+        n = int(rng.choice([1, 2, 3, 4, 7, 31, 64, 255, 256, 257, 600, 2000]))
+        mode = trial % 4
+        if mode == 0:
+            pos = rng.random((3 * n, 3)).astype(np.float32)
+        elif mode == 1:
+            pos = np.round(rng.random((3 * n, 3)) * 4).astype(np.float32) / 4
+        elif mode == 2:
+            base = rng.random((max(1, n // 8) * 3, 3)).astype(np.float32)
+            pos = np.tile(base, (-(-n * 3 // len(base)), 1))[:3 * n].copy()
+        else:
+            pos = (rng.random((3 * n, 3)) * np.asarray([1000, 1e-3, 1])).astype(np.float32)
+        idx = np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)
+        sc = scenes.Scene("soup", [scenes.Mesh(np.ascontiguousarray(pos), idx, np.zeros(n, np.uint32))], np.asarray([[.8, .8, .8, .5, 0, 0, 0, 0]], np.float32))
+        v = pos[idx]
+        box = np.ascontiguousarray(np.concatenate([v.min(1), v.max(1)], 1), np.float32)
+        cent = np.ascontiguousarray(((v[:, 0] + v[:, 1]) + v[:, 2]) * np.float32(0.333333343267440796), np.float32)
+        lo = np.zeros(3, np.float32); hi = np.zeros(3, np.float32)
+        for leaf in (1, 3):
+            on, ot, oo = OracleScene(sc, max_leaf=leaf).blas(0)
+            for tile in (0, 2, 7, 64, 256):
+                nodes = np.zeros(n + 1, NODE_DTYPE); seq = np.zeros(n, np.uint32); order = np.zeros(n, np.uint32)
+                if tile == 0:
+                    nn = E.emu_build(_p(box), _p(cent), C.c_uint32(n), C.c_uint32(leaf), _p(lo), _p(hi), _p(nodes), _p(seq), _p(order))
+                else:
+                    nn = E.emu_build_agglomerative(_p(box), _p(cent), C.c_uint32(n), C.c_uint32(leaf), _p(lo), _p(hi), _p(nodes), _p(seq), _p(order), C.c_uint32(tile))
+                assert nn == len(on) and nodes[:nn].tobytes() == on.tobytes() and np.array_equal(order, oo), (trial, n, mode, leaf, tile)
