@@ -4,6 +4,9 @@
 // the wavefront render loop (the slot of Renderer::Record's pass body, Renderer.cpp:332-351) and the
 // explicit-ray-set interface used for parity and the Mrays/s metric.
 // There is NO CPU fallback: without a CUDA device foundation_pt_create fails with FOUNDATION_PT_ERR_NO_DEVICE.
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the NCCL entry points are resolved at run time (dlopen), the library has no link-time NCCL dependency
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -112,6 +115,7 @@ struct foundation_pt_context {
     foundation_pt_config cfg{};
     foundation_pt_allocator host_alloc{};
     int device = 0, num_sms = 0, trace_blocks_per_sm = 0 /* 0 = kernel's own: 8 flat, 6 two-level */, fetch_thresh = 24;
+    int refit_blocks = 0;   // occupancy of the tiled refit kernel on this context's device (queried at the first build)
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // compute, H2D, D2H
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     mutable std::string err = "no error";
@@ -147,6 +151,13 @@ struct foundation_pt_context {
 
     // explicit ray set
     DevBuf d_rays, d_hits, d_hit_inst, d_occ; uint64_t num_rays = 0;
+
+    // multi-GPU frame (stage C1): communicator over the ranks that share one frame
+    ncclComm_t comm = nullptr; uint32_t comm_rank = 0, comm_count = 1, comm_flags = 0; bool comm_owned = false;
+    float4* remote_accum = nullptr; bool remote_is_ipc = false;     // direct mode: the root's accumulation buffer as seen from this device
+    DevBuf d_pack, d_stage, d_stage_off, d_row_base, d_comm_scratch;
+    std::vector<uint32_t> rank_pixels, stage_off;
+    float gather_ms = 0;
 
     foundation_pt_stats stats{};
     uint64_t total_launches = 0; uint32_t call_launches = 0;
@@ -250,7 +261,7 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
         DevBuf up_list, up_count;   // freed stream-ordered when the scope ends
         PT_CK(up_list.alloc((size_t)n * 4)); PT_CK(up_count.alloc(16));
         PT_CK(cudaMemsetAsync(up_count.p, 0, 4, ctx->stream));
-        static int refit_blocks = 0;     // resident blocks per SM (shared-memory bound): the grid is exactly one wave, tiles are strided over it
+        int& refit_blocks = ctx->refit_blocks;     // resident blocks per SM (shared-memory bound), per context / device: the grid is exactly one wave, tiles are strided over it
 #if PT_AGGLOMERATIVE
         if (!refit_blocks && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&refit_blocks, k_refit_agg, PT_REFIT_TILE, 0) != cudaSuccess || refit_blocks < 1)) { cudaGetLastError(); refit_blocks = 4; }
         PT_LAUNCH(ctx, k_refit_agg, grid_for(ctx, n, PT_REFIT_TILE, (uint32_t)refit_blocks), PT_REFIT_TILE, b, keys.as<uint64_t>(), d_prim_box, vals.as<uint32_t>(),
@@ -412,7 +423,7 @@ int32_t setup_wave(Ctx* ctx) {
         PT_CK(cudaStreamSynchronize(ctx->stream));
     } else { ctx->num_slots = W * H; ctx->w_slot_pixel.release(); }
     // several samples per wave: more rays in flight per launch and fewer launches per sample (results unchanged: one slot per
-    // (pixel, sample), accumulated in sample order).  Capped at 8 samples / 16 M slots.
+    // (pixel, sample), accumulated in sample order).  Capped at 64 samples / 16 M slots.
     ctx->wave_samples = 1;
     if (ctx->num_slots) { uint64_t k = (16ull << 20) / ctx->num_slots; ctx->wave_samples = (uint32_t)(k < 1 ? 1 : (k > 64 ? 64 : k)); }
     if (const char* e = getenv("FOUNDATION_PT_WAVE_SAMPLES")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->wave_samples = v; }
@@ -485,11 +496,148 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
             mark(3);
             std::swap(w.active, w.next);
         }
-        PT_LAUNCH(ctx, k_accumulate, grid_for(ctx, ctx->num_slots, 256, 8), 256, w, ctx->d_accum.as<float4>());
+        PT_LAUNCH(ctx, k_accumulate, grid_for(ctx, ctx->num_slots, 256, 8), 256, w, ctx->d_accum.as<float4>(),
+                  (ctx->comm_count > 1 && (ctx->comm_flags & FOUNDATION_PT_COMM_DIRECT) && ctx->comm_rank != 0) ? ctx->remote_accum : nullptr);
         mark(5);
     }
     PT_CK(cudaGetLastError());
     return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// C1: NCCL, resolved at run time.  libfoundation_pt.so has no link-time NCCL dependency: a single-GPU host never loads it, and a
+// process that already carries an NCCL (e.g. the one bundled with torch) shares that copy (same SONAME).
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr; std::string err;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr; decltype(&ncclCommInitRank) CommInitRank = nullptr; decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr; decltype(&ncclGroupStart) GroupStart = nullptr; decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclSend) Send = nullptr; decltype(&ncclRecv) Recv = nullptr; decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr; decltype(&ncclGetErrorString) GetErrorString = nullptr; decltype(&ncclGetVersion) GetVersion = nullptr;
+    bool ok() const { return lib != nullptr && err.empty(); }
+};
+const NcclApi& nccl_api() {
+    static const NcclApi api = [] {
+        NcclApi a;
+        const char* names[] = {getenv("FOUNDATION_PT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { if (n && *n && (a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break; }
+        if (!a.lib) { a.err = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found"); return a; }
+#define PT_NCCL_SYM(field, sym) do { a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.lib, #sym)); if (!a.field) a.err = "libnccl lacks " #sym; } while (0)
+        PT_NCCL_SYM(GetUniqueId, ncclGetUniqueId); PT_NCCL_SYM(CommInitRank, ncclCommInitRank); PT_NCCL_SYM(CommInitAll, ncclCommInitAll);
+        PT_NCCL_SYM(CommDestroy, ncclCommDestroy); PT_NCCL_SYM(GroupStart, ncclGroupStart); PT_NCCL_SYM(GroupEnd, ncclGroupEnd);
+        PT_NCCL_SYM(Send, ncclSend); PT_NCCL_SYM(Recv, ncclRecv); PT_NCCL_SYM(AllReduce, ncclAllReduce); PT_NCCL_SYM(Broadcast, ncclBroadcast);
+        PT_NCCL_SYM(GetErrorString, ncclGetErrorString); PT_NCCL_SYM(GetVersion, ncclGetVersion);
+#undef PT_NCCL_SYM
+        return a;
+    }();
+    return api;
+}
+#define PT_NCCL(expr)                                                                                                      \
+    do {                                                                                                                   \
+        ncclResult_t r_ = (expr);                                                                                          \
+        if (r_ != ncclSuccess) return ctx->fail(FOUNDATION_PT_ERR_COMM, std::string(#expr) + ": " + nccl_api().GetErrorString(r_)); \
+    } while (0)
+
+// Pixels every rank owns, and for the root the tables k_unpack_gathered needs: row_base[r][y] = pixels of rank r in the rows above y,
+// stage_off[r] = where rank r's block starts in the root's staging buffer.  Same ownership rule as setup_wave.
+int32_t plan_gather(Ctx* ctx) {
+    const uint32_t W = ctx->cfg.width, H = ctx->cfg.height, T = ctx->part_tile ? ctx->part_tile : 32, N = ctx->part_count;
+    const uint32_t tiles_x = (W + T - 1) / T;
+    std::vector<uint32_t> row_base((size_t)N * H);
+    ctx->rank_pixels.assign(N, 0);
+    for (uint32_t y = 0; y < H; ++y) {
+        const uint32_t ty = y / T;
+        for (uint32_t r = 0; r < N; ++r) row_base[(size_t)r * H + y] = ctx->rank_pixels[r];
+        for (uint32_t tx = 0; tx < tiles_x; ++tx) ctx->rank_pixels[(tx + ty) % N] += std::min(T, W - tx * T);
+    }
+    ctx->stage_off.assign(N, 0);
+    uint32_t off = 0;
+    for (uint32_t r = 0; r < N; ++r) { ctx->stage_off[r] = off; off += ctx->rank_pixels[r]; }   // the root's own slot stays unused: offsets are root-independent
+    PT_CK(ctx->d_row_base.alloc(row_base.size() * 4)); PT_CK(ctx->d_stage_off.alloc((size_t)N * 4));
+    PT_CK(cudaMemcpyAsync(ctx->d_row_base.p, row_base.data(), row_base.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaMemcpyAsync(ctx->d_stage_off.p, ctx->stage_off.data(), (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(ctx->d_comm_scratch.alloc(256));
+    PT_CK(cudaMemsetAsync(ctx->d_comm_scratch.p, 0, 256, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int32_t ensure_accum(Ctx* ctx) {
+    if (ctx->d_accum.p) return 0;
+    const size_t need = (size_t)ctx->cfg.width * ctx->cfg.height * 16;
+    PT_CK(ctx->d_accum.alloc(need));
+    PT_CK(cudaMemsetAsync(ctx->d_accum.p, 0, need, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Enqueues the gather of one frame on the streams of the `n` local members of a communicator (n = 1: one process per GPU; n = count:
+// a single-process group).  Stream-ordered behind whatever render is in flight; the caller synchronises.
+//   NCCL form:   pack owned pixels -> ncclSend to the root | root: ncclRecv every block -> scatter into the frame.
+//   direct form: the owners' accumulate kernels already stored their pixels into the root's frame over NVLink (k_accumulate `remote`),
+//                what is left is a barrier: a 4-byte all-reduce orders every rank's stores before the root's next read.
+int32_t gather_enqueue(Ctx** cs, uint32_t n, uint32_t root) {
+    const NcclApi& api = nccl_api();
+    Ctx* ctx = cs[0];
+    if (!api.ok()) return ctx->fail(FOUNDATION_PT_ERR_COMM, api.err);
+    for (uint32_t i = 0; i < n; ++i) { Ctx* c = cs[i]; if (!c->comm || root >= c->comm_count) return c->fail(FOUNDATION_PT_ERR_STATE, "gather: no communicator (comm_init / group_create first) or bad root"); }
+    const bool direct = (ctx->comm_flags & FOUNDATION_PT_COMM_DIRECT) != 0;
+    if (direct && root != 0) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "gather: direct mode gathers to rank 0");
+    for (uint32_t i = 0; i < n; ++i) {
+        ctx = cs[i];
+        PT_CK(cudaSetDevice(ctx->device));
+        int32_t rc = setup_wave(ctx);          // the owned-pixel list (slot order) lives with the wavefront state
+        if (rc) return rc;
+        PT_CK(cudaEventRecord(ctx->ev2, ctx->stream));
+        if (direct) continue;
+        if (ctx->comm_rank != root) {
+            PT_CK(ctx->d_pack.bytes >= (size_t)ctx->num_slots * 16 ? cudaSuccess : ctx->d_pack.alloc((size_t)ctx->num_slots * 16 + 16));
+            if (ctx->num_slots) PT_LAUNCH(ctx, k_pack_owned, grid_for(ctx, ctx->num_slots, 256, 8), 256, ctx->d_accum.as<float4>(), ctx->w_slot_pixel.as<uint32_t>(), ctx->num_slots, ctx->d_pack.as<float4>());
+        } else {
+            const size_t total = (size_t)ctx->stage_off.back() + ctx->rank_pixels.back();
+            if (ctx->d_stage.bytes < total * 16) PT_CK(ctx->d_stage.alloc(total * 16 + 16));
+        }
+    }
+    ctx = cs[0];
+    PT_NCCL(api.GroupStart());
+    for (uint32_t i = 0; i < n; ++i) {
+        Ctx* c = cs[i];
+        cudaSetDevice(c->device);
+        ncclResult_t r = ncclSuccess;
+        if (direct) r = api.AllReduce(c->d_comm_scratch.p, c->d_comm_scratch.as<float>() + 1, 1, ncclFloat32, ncclSum, c->comm, c->stream);
+        else if (c->comm_rank != root) { if (c->num_slots) r = api.Send(c->d_pack.p, (size_t)c->num_slots * 4, ncclFloat32, (int)root, c->comm, c->stream); }
+        else
+            for (uint32_t p = 0; p < c->comm_count && r == ncclSuccess; ++p)
+                if (p != root && c->rank_pixels[p]) r = api.Recv(c->d_stage.as<float4>() + c->stage_off[p], (size_t)c->rank_pixels[p] * 4, ncclFloat32, (int)p, c->comm, c->stream);
+        if (r != ncclSuccess) { api.GroupEnd(); return c->fail(FOUNDATION_PT_ERR_COMM, std::string("NCCL send/recv: ") + api.GetErrorString(r)); }
+    }
+    PT_NCCL(api.GroupEnd());
+    for (uint32_t i = 0; i < n; ++i) {
+        ctx = cs[i];
+        PT_CK(cudaSetDevice(ctx->device));
+        if (!direct && ctx->comm_rank == root) {
+            PtGatherPlan g; g.width = ctx->cfg.width; g.height = ctx->cfg.height; g.tile = ctx->part_tile ? ctx->part_tile : 32; g.count = ctx->comm_count; g.root = root; g.only = PT_NONE;
+            PT_LAUNCH(ctx, k_unpack_gathered, grid_for(ctx, (uint64_t)g.width * g.height, 256, 8), 256, g, ctx->d_stage.as<float4>(), ctx->d_stage_off.as<uint32_t>(),
+                      ctx->d_row_base.as<uint32_t>(), ctx->d_accum.as<float4>());
+        }
+        PT_CK(cudaEventRecord(ctx->ev3, ctx->stream));
+    }
+    return 0;
+}
+int32_t gather_finish(Ctx* ctx) {
+    PT_CK(cudaSetDevice(ctx->device));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->gather_ms = ms; else cudaGetLastError();
+    ctx->stats.gather_ms = ctx->gather_ms;
+    return 0;
+}
+void comm_release(Ctx* ctx) {
+    if (ctx->remote_accum && ctx->remote_is_ipc) cudaIpcCloseMemHandle(ctx->remote_accum);
+    ctx->remote_accum = nullptr; ctx->remote_is_ipc = false;
+    if (ctx->comm && ctx->comm_owned && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
+    ctx->comm = nullptr; ctx->comm_owned = false; ctx->comm_count = 1; ctx->comm_rank = 0; ctx->comm_flags = 0;
+    cudaGetLastError();
 }
 
 }  // namespace
@@ -518,6 +666,9 @@ int32_t foundation_pt_create(const foundation_pt_config* config, const foundatio
     if (!config || config->struct_size != sizeof(foundation_pt_config)) { g_create_error = "config NULL or struct_size mismatch"; return FOUNDATION_PT_ERR_ARGUMENT; }
     if (config->width == 0 || config->height == 0 || (uint64_t)config->width * config->height > (1ull << 30)) { g_create_error = "bad render target size"; return FOUNDATION_PT_ERR_ARGUMENT; }
     if (config->max_leaf_tris > 3) { g_create_error = "max_leaf_tris must be 0..3"; return FOUNDATION_PT_ERR_ARGUMENT; }
+    if (host_alloc && ((host_alloc->alloc != nullptr) != (host_alloc->free != nullptr))) {
+        g_create_error = "host allocator must provide both alloc and free (or neither)"; return FOUNDATION_PT_ERR_ARGUMENT;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -563,6 +714,7 @@ int32_t foundation_pt_destroy(foundation_pt_context* ctx) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    comm_release(ctx);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -787,7 +939,8 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
         else add_mesh_lights(0, nullptr);
     }
     ctx->num_lights = (uint32_t)lights.size();
-    ctx->light_area = pt_lights_finalize(lights.data(), ctx->num_lights);
+    ctx->light_area = pt_lights_finalize(lights.data(), &ctx->num_lights);   // degenerate emitters are dropped here
+    lights.resize(ctx->num_lights);
     PT_CK(ctx->d_lights.alloc(lights.size() * sizeof(PtLight)));
     if (!lights.empty()) PT_CK(cudaMemcpyAsync(ctx->d_lights.p, lights.data(), lights.size() * sizeof(PtLight), cudaMemcpyHostToDevice, ctx->stream));
     PT_CK(ctx->d_mats.alloc(ctx->mats.size() * sizeof(PtMaterial)));
@@ -826,6 +979,7 @@ int32_t foundation_pt_partition_set(foundation_pt_context* ctx, uint32_t rank, u
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
     settle(ctx);
     if (count == 0 || rank >= count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "partition_set: rank must be < count");
+    if (ctx->comm && (rank != ctx->comm_rank || count != ctx->comm_count)) return ctx->fail(FOUNDATION_PT_ERR_STATE, "partition_set: the partition of a communicator member is fixed by comm_init / group_create");
     ctx->part_rank = rank; ctx->part_count = count; ctx->part_tile = tile_size ? tile_size : 32;
     ctx->wave_ready = false;
     return FOUNDATION_PT_OK;
@@ -838,13 +992,22 @@ int32_t foundation_pt_render_async(foundation_pt_context* ctx, uint32_t sample_b
     if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "render: scene not committed");
     if (!ctx->cam_set) return ctx->fail(FOUNDATION_PT_ERR_STATE, "render: camera not set");
     if (max_bounces > 64) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "render: max_bounces > 64");
+    // the PCG stream id is (sample << 32 | pixel) << 1 | 1: bit 31 of the sample index would be shifted out and alias an earlier sample,
+    // and a 32-bit sample_begin + sample_count must not wrap
+    if ((uint64_t)sample_begin + sample_count > (1ull << 31)) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "render: sample_begin + sample_count must not exceed 2^31");
     if (ctx->render_pending) return ctx->fail(FOUNDATION_PT_ERR_STATE, "render_async: the previous asynchronous render has not been waited for");
     PT_TRY
     cudaSetDevice(ctx->device);
     int32_t rc = setup_wave(ctx);
     if (rc) return rc;
     begin_call(ctx);
-    if (sample_begin == 0) PT_CK(cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)ctx->cfg.width * ctx->cfg.height * 16, ctx->stream));
+    if (sample_begin == 0) {
+        // direct mode: the pixels of the root's frame that belong to other ranks are written by THEIR accumulate kernels over NVLink,
+        // possibly before this stream gets here — every rank clears only the pixels it owns
+        if (ctx->comm_count > 1 && (ctx->comm_flags & FOUNDATION_PT_COMM_DIRECT)) {
+            if (ctx->num_slots) PT_LAUNCH(ctx, k_clear_owned, grid_for(ctx, ctx->num_slots, 256, 8), 256, ctx->d_accum.as<float4>(), ctx->w_slot_pixel.as<uint32_t>(), ctx->num_slots);
+        } else PT_CK(cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)ctx->cfg.width * ctx->cfg.height * 16, ctx->stream));
+    }
     PT_CK(cudaMemsetAsync(ctx->w_ctr.p, 0, sizeof(PtWaveCounters), ctx->stream));
     if (ctx->num_slots) {
         rc = ctx->two_level ? render_impl<true>(ctx, sample_begin, sample_count, max_bounces) : render_impl<false>(ctx, sample_begin, sample_count, max_bounces);
@@ -1081,6 +1244,199 @@ int32_t foundation_pt_tlas_download(foundation_pt_context* ctx, void* nodes, siz
     if (nodes) { if (nodes_bytes < (size_t)ctx->tlas_nodes * 80) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "tlas_download: nodes buffer too small"); PT_CK(cudaMemcpy(nodes, ctx->d_nodes_all.as<PtNode8>() + ctx->view.tlas_base, (size_t)ctx->tlas_nodes * 80, cudaMemcpyDeviceToHost)); }
     if (order) { if (order_bytes < (size_t)ctx->num_inst * 4) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "tlas_download: order buffer too small"); PT_CK(cudaMemcpy(order, ctx->d_tlas_order.p, (size_t)ctx->num_inst * 4, cudaMemcpyDeviceToHost)); }
     return FOUNDATION_PT_OK;
+}
+
+
+// ---- multi-GPU frame (stage C1) ---------------------------------------------------------------------------
+int32_t foundation_pt_comm_unique_id(uint8_t* id, size_t size_bytes) {
+    if (!id || size_bytes < FOUNDATION_PT_COMM_ID_BYTES) { g_create_error = "comm_unique_id: buffer smaller than FOUNDATION_PT_COMM_ID_BYTES"; return FOUNDATION_PT_ERR_ARGUMENT; }
+    const NcclApi& api = nccl_api();
+    if (!api.ok()) { g_create_error = api.err; return FOUNDATION_PT_ERR_COMM; }
+    static_assert(sizeof(ncclUniqueId) == FOUNDATION_PT_COMM_ID_BYTES, "NCCL unique id size");
+    ncclUniqueId u;
+    ncclResult_t r = api.GetUniqueId(&u);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + api.GetErrorString(r); return FOUNDATION_PT_ERR_COMM; }
+    memcpy(id, &u, sizeof u);
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_comm_init(foundation_pt_context* ctx, const uint8_t* id, size_t size_bytes, uint32_t rank, uint32_t count, uint32_t tile_size, uint32_t flags) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
+    if (!id || size_bytes < FOUNDATION_PT_COMM_ID_BYTES || count == 0 || rank >= count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "comm_init: bad id / rank / count");
+    if (ctx->comm) return ctx->fail(FOUNDATION_PT_ERR_STATE, "comm_init: this context already belongs to a communicator");
+    const NcclApi& api = nccl_api();
+    if (!api.ok()) return ctx->fail(FOUNDATION_PT_ERR_COMM, api.err);
+    PT_TRY
+    PT_CK(cudaSetDevice(ctx->device));
+    ncclUniqueId u; memcpy(&u, id, sizeof u);
+    PT_NCCL(api.CommInitRank(&ctx->comm, (int)count, u, (int)rank));
+    ctx->comm_owned = true; ctx->comm_rank = rank; ctx->comm_count = count; ctx->comm_flags = flags;
+    ctx->part_rank = rank; ctx->part_count = count; ctx->part_tile = tile_size ? tile_size : 32; ctx->wave_ready = false;
+    int32_t rc = ensure_accum(ctx);
+    if (!rc) rc = plan_gather(ctx);
+    if (rc) { comm_release(ctx); return rc; }
+    if ((flags & FOUNDATION_PT_COMM_DIRECT) && count > 1) {
+        // the root's frame, mapped into every other rank's address space: IPC handle broadcast over the communicator itself
+        cudaIpcMemHandle_t h; memset(&h, 0, sizeof h);
+        static_assert(sizeof(cudaIpcMemHandle_t) <= 128, "IPC handle fits the scratch buffer");
+        if (rank == 0) {
+            cudaError_t e = cudaIpcGetMemHandle(&h, ctx->d_accum.p);
+            if (e != cudaSuccess) { cudaGetLastError(); memset(&h, 0, sizeof h); }   // all-zero handle = "no IPC": every rank then fails alike instead of hanging
+            PT_CK(cudaMemcpyAsync(ctx->d_comm_scratch.as<uint8_t>() + 64, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        PT_NCCL(api.Broadcast(ctx->d_comm_scratch.as<uint8_t>() + 64, ctx->d_comm_scratch.as<uint8_t>() + 64, sizeof h, ncclUint8, 0, ctx->comm, ctx->stream));
+        PT_CK(cudaMemcpyAsync(&h, ctx->d_comm_scratch.as<uint8_t>() + 64, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        PT_CK(cudaStreamSynchronize(ctx->stream));
+        bool zero = true; for (size_t k = 0; k < sizeof h; ++k) zero &= reinterpret_cast<const uint8_t*>(&h)[k] == 0;
+        if (zero) { comm_release(ctx); return ctx->fail(FOUNDATION_PT_ERR_COMM, "comm_init: the root could not export its frame (cudaIpcGetMemHandle)"); }
+        if (rank != 0) {
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { cudaGetLastError(); comm_release(ctx); return ctx->fail(FOUNDATION_PT_ERR_COMM, std::string("comm_init: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+            ctx->remote_accum = static_cast<float4*>(p); ctx->remote_is_ipc = true;
+        }
+    }
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_gather(foundation_pt_context* ctx, uint32_t root) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
+    PT_TRY
+    if (ctx->comm_count <= 1 && ctx->comm) return FOUNDATION_PT_OK;
+    ctx->call_launches = 0;
+    int32_t rc = gather_enqueue(&ctx, 1, root);
+    if (rc) return rc;
+    rc = gather_finish(ctx);
+    ctx->stats.kernel_launches = ctx->call_launches; ctx->stats.total_launches = ctx->total_launches;
+    return rc;
+    PT_CATCH(ctx)
+}
+
+
+// Same-device form of the gather: several partitions of one frame rendered by several contexts on ONE device (tests on a single-GPU
+// box; also a way to split a frame over streams).  Scatters src's owned tiles into dst's frame with the same pack / scatter kernels
+// as the NCCL form, a device-to-device copy standing in for ncclSend / ncclRecv.
+int32_t foundation_pt_gather_local(foundation_pt_context* dst, foundation_pt_context* src) {
+    if (!dst || !src) return FOUNDATION_PT_ERR_ARGUMENT;
+    foundation_pt_context* ctx = dst;
+    settle(dst); settle(src);
+    if (dst == src || dst->device != src->device || dst->part_count != src->part_count || dst->part_tile != src->part_tile || dst->cfg.width != src->cfg.width ||
+        dst->cfg.height != src->cfg.height || dst->part_rank == src->part_rank || dst->part_count < 2)
+        return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "gather_local: the two contexts must be different partitions (same count / tile / frame size) on the same device");
+    PT_TRY
+    PT_CK(cudaSetDevice(dst->device));
+    int32_t rc = setup_wave(src);
+    if (rc) { dst->err = src->err; return rc; }
+    if (dst->rank_pixels.size() != dst->part_count) { rc = ensure_accum(dst); if (!rc) rc = plan_gather(dst); if (rc) return rc; }
+    dst->call_launches = 0;
+    const size_t total = (size_t)dst->stage_off.back() + dst->rank_pixels.back();
+    if (dst->d_stage.bytes < total * 16) PT_CK(dst->d_stage.alloc(total * 16 + 16));
+    if (src->d_pack.bytes < (size_t)src->num_slots * 16) { ctx = src; PT_CK(src->d_pack.alloc((size_t)src->num_slots * 16 + 16)); ctx = dst; }
+    if (src->num_slots) {
+        k_pack_owned<<<grid_for(src, src->num_slots, 256, 8), 256, 0, src->stream>>>(src->d_accum.as<float4>(), src->w_slot_pixel.as<uint32_t>(), src->num_slots, src->d_pack.as<float4>());
+        dst->call_launches++; dst->total_launches++;
+        PT_CK(cudaMemcpyAsync(dst->d_stage.as<float4>() + dst->stage_off[src->part_rank], src->d_pack.p, (size_t)src->num_slots * 16, cudaMemcpyDeviceToDevice, src->stream));
+    }
+    PT_CK(cudaStreamSynchronize(src->stream));
+    if (src->num_slots != dst->rank_pixels[src->part_rank]) return ctx->fail(FOUNDATION_PT_ERR_STATE, "gather_local: partition plans disagree");
+    PtGatherPlan g; g.width = dst->cfg.width; g.height = dst->cfg.height; g.tile = dst->part_tile ? dst->part_tile : 32; g.count = dst->part_count; g.root = dst->part_rank; g.only = src->part_rank;
+    PT_LAUNCH(dst, k_unpack_gathered, grid_for(dst, (uint64_t)g.width * g.height, 256, 8), 256, g, dst->d_stage.as<float4>(), dst->d_stage_off.as<uint32_t>(),
+              dst->d_row_base.as<uint32_t>(), dst->d_accum.as<float4>());
+    PT_CK(cudaStreamSynchronize(dst->stream));
+    dst->stats.kernel_launches = dst->call_launches; dst->stats.total_launches = dst->total_launches;
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+}  // extern "C"
+
+// ---- single-process group: one host thread drives N devices (SURVEY.md section 8e "Process model") -----------------------
+struct foundation_pt_group {
+    std::vector<foundation_pt_context*> members;
+    std::string err = "no error";
+};
+
+extern "C" {
+
+int32_t foundation_pt_group_create(const foundation_pt_config* config, const int32_t* devices, uint32_t count, uint32_t tile_size, uint32_t flags,
+                                   const foundation_pt_allocator* host_alloc, foundation_pt_group** out_group) {
+    if (!out_group) { g_create_error = "out_group is NULL"; return FOUNDATION_PT_ERR_ARGUMENT; }
+    *out_group = nullptr;
+    if (!config || !devices || count == 0 || count > 64) { g_create_error = "group_create: bad config / device list"; return FOUNDATION_PT_ERR_ARGUMENT; }
+    foundation_pt_group* g = new (std::nothrow) foundation_pt_group();
+    if (!g) { g_create_error = "host allocation failed"; return FOUNDATION_PT_ERR_OOM; }
+    auto fail = [&](int32_t code, const std::string& msg) { g_create_error = msg; for (auto* m : g->members) foundation_pt_destroy(m); delete g; return code; };
+    for (uint32_t i = 0; i < count; ++i) {
+        foundation_pt_config c = *config; c.device = devices[i];
+        foundation_pt_context* m = nullptr;
+        int32_t rc = foundation_pt_create(&c, host_alloc, &m);
+        if (rc) return fail(rc, g_create_error);
+        g->members.push_back(m);
+    }
+    if (count > 1) {
+        const NcclApi& api = nccl_api();
+        if (!api.ok()) return fail(FOUNDATION_PT_ERR_COMM, api.err);
+        std::vector<ncclComm_t> comms(count);
+        std::vector<int> devs(devices, devices + count);
+        ncclResult_t r = api.CommInitAll(comms.data(), (int)count, devs.data());
+        if (r != ncclSuccess) return fail(FOUNDATION_PT_ERR_COMM, std::string("ncclCommInitAll: ") + api.GetErrorString(r));
+        for (uint32_t i = 0; i < count; ++i) {
+            Ctx* m = g->members[i];
+            m->comm = comms[i]; m->comm_owned = true; m->comm_rank = i; m->comm_count = count; m->comm_flags = flags;
+            m->part_rank = i; m->part_count = count; m->part_tile = tile_size ? tile_size : 32; m->wave_ready = false;
+            cudaSetDevice(m->device);
+            int32_t rc = ensure_accum(m);
+            if (!rc) rc = plan_gather(m);
+            if (rc) return fail(rc, m->err);
+        }
+        if (flags & FOUNDATION_PT_COMM_DIRECT) {
+            for (uint32_t i = 1; i < count; ++i) {
+                Ctx* m = g->members[i];
+                if (m->device != g->members[0]->device) {
+                    cudaSetDevice(m->device);
+                    cudaError_t e = cudaDeviceEnablePeerAccess(g->members[0]->device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return fail(FOUNDATION_PT_ERR_COMM, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); }
+                    cudaGetLastError();
+                }
+                m->remote_accum = g->members[0]->d_accum.as<float4>(); m->remote_is_ipc = false;
+            }
+        }
+    }
+    *out_group = g;
+    return FOUNDATION_PT_OK;
+}
+
+int32_t foundation_pt_group_destroy(foundation_pt_group* group) {
+    if (!group) return FOUNDATION_PT_ERR_ARGUMENT;
+    for (auto* m : group->members) { cudaSetDevice(m->device); if (m->stream) cudaStreamSynchronize(m->stream); }
+    for (auto* m : group->members) foundation_pt_destroy(m);
+    delete group;
+    return FOUNDATION_PT_OK;
+}
+uint32_t foundation_pt_group_size(const foundation_pt_group* group) { return group ? (uint32_t)group->members.size() : 0u; }
+foundation_pt_context* foundation_pt_group_context(foundation_pt_group* group, uint32_t index) {
+    return (group && index < group->members.size()) ? group->members[index] : nullptr;
+}
+const char* foundation_pt_group_last_error(const foundation_pt_group* group) { return group ? group->err.c_str() : g_create_error.c_str(); }
+
+int32_t foundation_pt_group_render(foundation_pt_group* group, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces) {
+    if (!group) return FOUNDATION_PT_ERR_ARGUMENT;
+    auto fail = [&](int32_t rc, foundation_pt_context* m) { group->err = m->err; for (auto* o : group->members) foundation_pt_wait(o); return rc; };
+    for (auto* m : group->members) { int32_t rc = foundation_pt_render_async(m, sample_begin, sample_count, max_bounces); if (rc) return fail(rc, m); }
+    if (group->members.size() > 1) {
+        int32_t rc = gather_enqueue(group->members.data(), (uint32_t)group->members.size(), 0);
+        if (rc) return fail(rc, group->members[0]);
+    }
+    int32_t first = FOUNDATION_PT_OK;
+    for (auto* m : group->members) {
+        int32_t rc = foundation_pt_wait(m);
+        if (!rc && group->members.size() > 1) rc = gather_finish(m);
+        if (rc && !first) { first = rc; group->err = m->err; }
+    }
+    return first;
 }
 
 }  // extern "C"

@@ -96,13 +96,18 @@ PT_HD float pt_light_make(PtLight* l, pt_v3 v0, pt_v3 e1, pt_v3 e2, float er, fl
     l->emr = er; l->emg = eg; l->emb = eb; l->pad1 = 0.0f;
     return area;
 }
-// cumulative area fractions (sequential double prefix, rounded once); returns the total area as float
-static inline float pt_lights_finalize(PtLight* l, uint32_t n) {
+// Drops degenerate emitters (area not > 0: a zero-area or NaN triangle would put NaN into every cdf and, with a total area of 0,
+// inf / NaN into the NEE pdf), then writes the cumulative area fractions (sequential double prefix, rounded once).  *n is updated to
+// the number of lights kept; returns the total area as float (0 when no light is left: callers then run without NEE).
+static inline float pt_lights_finalize(PtLight* l, uint32_t* n) {
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < *n; ++i) if (l[i].area > 0.0f && l[i].area < 3.0e38f) l[m++] = l[i];
+    *n = m;
     double total = 0.0;
-    for (uint32_t i = 0; i < n; ++i) total += (double)l[i].area;
+    for (uint32_t i = 0; i < m; ++i) total += (double)l[i].area;
     double run = 0.0;
-    for (uint32_t i = 0; i < n; ++i) { run += (double)l[i].area; l[i].cdf = (float)(run / total); }
-    if (n) l[n - 1].cdf = 1.0f;
-    return (float)total;
+    for (uint32_t i = 0; i < m; ++i) { run += (double)l[i].area; l[i].cdf = (float)(run / total); }
+    if (m) l[m - 1].cdf = 1.0f;
+    return m ? (float)total : 0.0f;
 }
 #define PT_RAY_EPS_REL 1.52587890625e-05f  // 2^-16 x largest world extent: secondary-ray origin offset

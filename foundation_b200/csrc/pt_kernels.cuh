@@ -1111,8 +1111,12 @@ __global__ void k_bounce_end(PtWave w) {
     w.ctr->n_active = w.ctr->n_next; w.ctr->n_next = 0; w.ctr->n_shadow = 0; w.ctr->work_extend = 0; w.ctr->work_connect = 0;
 }
 
-// B7: accumulate the wave's samples into the frame (one add per pixel per sample, in sample order: deterministic)
-__global__ void __launch_bounds__(256) k_accumulate(PtWave w, float4* accum) {
+// B7: accumulate the wave's samples into the frame (one add per pixel per sample, in sample order: deterministic).
+// C1, fused form: when this context is a non-root member of a multi-GPU frame in direct mode, `remote` is the ROOT's accumulation buffer
+// mapped into this device's address space (peer access inside one process, CUDA IPC across processes).  The finished sum of every
+// owned pixel is stored there too, so the gather over NVLink happens tile by tile inside the producing kernel and the collective
+// that follows is only a barrier.  Remote stores only (no remote read): the owner keeps the master copy.
+__global__ void __launch_bounds__(256) k_accumulate(PtWave w, float4* accum, float4* remote) {
     const uint32_t samples = w.num_slots / w.num_pixels;
     for (uint32_t ps = pt_gtid(); ps < w.num_pixels; ps += pt_gsize()) {
         uint32_t pixel = w.slot_pixel ? w.slot_pixel[ps] : ps;
@@ -1122,6 +1126,34 @@ __global__ void __launch_bounds__(256) k_accumulate(PtWave w, float4* accum) {
             a = make_float4(a.x + L.x, a.y + L.y, a.z + L.z, a.w + 1.0f);
         }
         accum[pixel] = a;
+        if (remote) remote[pixel] = a;
+    }
+}
+// zero the owned pixels only (direct mode: the other pixels of the root's frame belong to their owners' remote stores)
+__global__ void __launch_bounds__(256) k_clear_owned(float4* accum, const uint32_t* slot_pixel, uint32_t n) {
+    for (uint32_t i = pt_gtid(); i < n; i += pt_gsize()) accum[slot_pixel[i]] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C1: gather of the tile-partitioned frame (NCCL form).  A rank packs its owned pixels in slot order (= scanline order of the owned
+// pixels), sends them to the root with ncclSend; the root receives every rank's block and scatters it into its frame.  The root
+// needs no per-rank pixel list: the position of pixel (x, y) inside its owner's block follows from the tile rule — row_base[r][y]
+// pixels of rank r lie in the rows above, and in row y the owner's tiles left of tile tx are all full width.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_owned(const float4* __restrict__ accum, const uint32_t* __restrict__ slot_pixel, uint32_t n, float4* __restrict__ out) {
+    for (uint32_t i = pt_gtid(); i < n; i += pt_gsize()) out[i] = accum[slot_pixel[i]];
+}
+struct PtGatherPlan { uint32_t width, height, tile, count, root, only /* PT_NONE = every rank but the root, else this rank's pixels only */; };
+__global__ void __launch_bounds__(256) k_unpack_gathered(PtGatherPlan g, const float4* __restrict__ stage, const uint32_t* __restrict__ stage_off /* [count] */,
+                                                         const uint32_t* __restrict__ row_base /* [count][height] */, float4* __restrict__ accum) {
+    const uint32_t n = g.width * g.height;
+    for (uint32_t p = pt_gtid(); p < n; p += pt_gsize()) {
+        const uint32_t x = p % g.width, y = p / g.width, tx = x / g.tile, ty = y / g.tile;
+        const uint32_t r = (tx + ty) % g.count;
+        if (r == g.root || (g.only != PT_NONE && r != g.only)) continue;
+        const uint32_t a = (r + g.count - ty % g.count) % g.count;            // first tile column of rank r in this tile row
+        const uint32_t before = tx > a ? (tx - a - 1u) / g.count + 1u : 0u;   // owned tiles left of tx (all full width)
+        accum[p] = stage[stage_off[r] + row_base[r * g.height + y] + before * g.tile + (x - tx * g.tile)];
     }
 }
 __global__ void __launch_bounds__(256) k_resolve_rgba8(const float4* accum, uint32_t n, uint32_t* out) {

@@ -1,15 +1,19 @@
-"""Multi-GPU sharding of the path-tracing pass: one process per GPU, `torch.distributed` for the plumbing.
+"""Multi-GPU sharding of the path-tracing pass for the one-process-per-GPU host shape (torchrun).
 
 SURVEY.md §8e: pixels and samples are independent, the scene is replicated per GPU (every rank runs the same
 deterministic build), the frame is split into interleaved 32x32 tiles (tile (tx,ty) -> rank (tx+ty) % world,
-the same rule as `foundation_pt_partition_set`), and the only exchange step is a sum-reduce of the float4
-accumulation buffer to rank 0 over NCCL / NVLink.  Ranks write disjoint pixels into zero-initialised frames,
-so the reduce adds exact zeros and the result is bit-identical to the single-GPU frame.
-The explicit-ray-set metric needs no collective at all: each rank traces its own slice.
+the same rule as `foundation_pt_partition_set`), and the only exchange step is the gather of the owned tiles
+into rank 0's accumulation buffer.  That exchange lives INSIDE the C ABI (`foundation_pt_comm_init` /
+`foundation_pt_gather`: packed ncclSend/ncclRecv, or — COMM_DIRECT — the accumulate kernel storing straight into
+rank 0's frame over NVLink peer memory); `torch.distributed` is used here only to hand the 128-byte communicator
+id from rank 0 to the other ranks and for the bench's barriers.  The gathered frame is bit-identical to the
+single-GPU frame.  The explicit-ray-set metric needs no collective at all: each rank traces its own slice.
+
+`reduce_frames` (a torch sum-reduce of whole zero-padded frames, round 1's gather) is kept as the host-side
+model of the exchange for the CPU tier (gloo, world size 2) — the product path no longer calls it.
 
 The reference is single-device (mos9527/Foundation src/Editor/Editor.cpp:18 takes EnumerateDevices()[0]), so
-nothing here replaces a reference interface; torch is used only for process-group plumbing and as the owner of
-the reduce's output tensor.
+nothing here replaces a reference interface.
 """
 from __future__ import annotations
 
@@ -85,15 +89,49 @@ def reduce_frames(local_frame, dst: int = 0):
     return out if dist.get_rank() == dst else None
 
 
-class DistributedRenderer:
-    """Tile-sharded progressive render over all ranks of the process group."""
+def packed_index(x, y, rank: int, world: int, width: int, height: int, tile: int = 32):
+    """Position of owned pixel (x, y) inside rank `rank`'s packed block (scanline order of its owned pixels) — the host-side
+    statement of what k_unpack_gathered computes on the root (row base from the rows above + full tiles to the left)."""
+    x = np.asarray(x, np.int64); y = np.asarray(y, np.int64)
+    tiles_x = (width + tile - 1) // tile
+    tx_all = np.arange(tiles_x)
+    tw = np.minimum(tile, width - tx_all * tile)
+    row_count = np.asarray([tw[(tx_all + ty) % world == rank].sum() for ty in range((height + tile - 1) // tile)], np.int64)   # per tile row
+    rows = row_count[np.arange(height) // tile]
+    base = np.concatenate([[0], np.cumsum(rows)[:-1]])
+    tx, ty = x // tile, y // tile
+    a = (rank - ty) % world
+    before = np.where(tx > a, (tx - a - 1) // world + 1, 0)
+    return base[y] + before * tile + (x - tx * tile)
 
-    def __init__(self, tracer, rank: int, world: int, tile: int = 32):
+
+def share_comm_id(make_id):
+    """Rank 0 calls make_id() (PathTracer.comm_unique_id); every rank returns the same 128 bytes."""
+    import torch.distributed as dist
+
+    rank, world, _ = env_rank_world()
+    if world == 1 or not dist.is_initialized():
+        return make_id()
+    box = [make_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+class DistributedRenderer:
+    """Tile-sharded progressive render over all ranks of the process group; the gather runs inside the C ABI."""
+
+    def __init__(self, tracer, rank: int, world: int, tile: int = 32, direct: bool = False):
+        from . import pt
+
         self.tracer, self.rank, self.world = tracer, rank, world
-        tracer.partition_set(rank, world, tile)
+        if world > 1:
+            cid = share_comm_id(pt.PathTracer.comm_unique_id)
+            tracer.comm_init(cid, rank, world, tile, pt.COMM_DIRECT if direct else 0)
+        else:
+            tracer.partition_set(0, 1, tile)
 
     def render(self, sample_begin: int, sample_count: int, max_bounces: int, gather: bool = True):
+        """Renders this rank's tiles; with gather=True rank 0's accumulation buffer then holds the whole frame."""
         self.tracer.render(sample_begin, sample_count, max_bounces)
-        if not gather:
-            return None
-        return reduce_frames(accum_as_tensor(self.tracer), 0)
+        if gather and self.world > 1:
+            self.tracer.gather(0)

@@ -16,7 +16,8 @@ import numpy as np
 from . import build as _build
 from .scenes import HIT_DTYPE, RAY_DTYPE, Scene  # noqa: F401
 
-OK, ERR_ARGUMENT, ERR_STATE, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_ARGUMENT, ERR_STATE, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_COMM = 0, -1, -2, -3, -4, -5, -6, -7
+COMM_ID_BYTES, COMM_DIRECT = 128, 1
 FLAG_NO_MATERIAL_SORT, FLAG_NO_NEE, FLAG_NO_BSDF_EMISSION, FLAG_MATERIAL_SORT, FLAG_SOBOL_JITTER, FLAG_SOBOL_PATH, FLAG_STAGE_TIMING = 1, 2, 4, 8, 16, 32, 64
 STAGE_NAMES = ("raygen", "extend", "shade", "connect", "material_sort", "accumulate")
 
@@ -38,7 +39,7 @@ class BuildStats(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("kernel_launches", C.c_uint32), ("rays_extend", C.c_uint64), ("rays_shadow", C.c_uint64),
-                ("last_ms", C.c_float), ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("reserved", C.c_uint32), ("total_launches", C.c_uint64),
+                ("last_ms", C.c_float), ("trace_ms", C.c_float), ("gather_ms", C.c_float), ("reserved", C.c_uint32), ("total_launches", C.c_uint64),
                 ("stage_ms", C.c_float * 6)]
 
 
@@ -71,6 +72,16 @@ SYMBOLS = {
     "foundation_pt_stats_get": (C.c_int32, [C.c_void_p, C.POINTER(Stats)]),
     "foundation_pt_blas_download": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "foundation_pt_comm_unique_id": (C.c_int32, [C.c_void_p, C.c_size_t]),
+    "foundation_pt_comm_init": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "foundation_pt_gather": (C.c_int32, [C.c_void_p, C.c_uint32]),
+    "foundation_pt_gather_local": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "foundation_pt_group_create": (C.c_int32, [C.POINTER(Config), C.POINTER(C.c_int32), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "foundation_pt_group_destroy": (C.c_int32, [C.c_void_p]),
+    "foundation_pt_group_size": (C.c_uint32, [C.c_void_p]),
+    "foundation_pt_group_context": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "foundation_pt_group_render": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "foundation_pt_group_last_error": (C.c_char_p, [C.c_void_p]),
     "foundation_pt_tlas_download": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
@@ -201,6 +212,30 @@ class PathTracer:
     def partition_set(self, rank: int, count: int, tile: int = 32):
         self._check(self._lib.foundation_pt_partition_set(self._ctx, rank, count, tile))
 
+    # -- multi-GPU frame (stage C1): one process per GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte communicator id (rank 0 creates it, the host distributes it to the other ranks by any channel)."""
+        lib = load_library()
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        st = lib.foundation_pt_comm_unique_id(buf, COMM_ID_BYTES)
+        if st != OK:
+            raise FoundationPtError(st, lib.foundation_pt_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, comm_id: bytes, rank: int, count: int, tile: int = 32, flags: int = 0):
+        """Collective over all ranks: joins the communicator and fixes this context's tile partition."""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+        self._check(self._lib.foundation_pt_comm_init(self._ctx, buf, COMM_ID_BYTES, rank, count, tile, flags))
+
+    def gather(self, root: int = 0):
+        """Collective: afterwards rank `root`'s accumulation buffer holds the whole frame."""
+        self._check(self._lib.foundation_pt_gather(self._ctx, root))
+
+    def gather_local(self, src: "PathTracer"):
+        """Same-device gather: scatters `src`'s owned tiles into this context's frame (no NCCL)."""
+        self._check(self._lib.foundation_pt_gather_local(self._ctx, src._ctx))
+
     # -- render
     def render(self, sample_begin: int, sample_count: int, max_bounces: int):
         self._check(self._lib.foundation_pt_render(self._ctx, sample_begin, sample_count, max_bounces))
@@ -322,3 +357,60 @@ class PathTracer:
         if nn.value:
             self._check(self._lib.foundation_pt_tlas_download(self._ctx, _p(nodes), nodes.nbytes, _p(order), order.nbytes, C.byref(nn), C.byref(ni)))
         return nodes, order
+
+
+class _Member(PathTracer):
+    """A context owned by a Group (borrowed handle: never destroyed on its own)."""
+
+    def __init__(self, lib, ctx, width, height, device):
+        self._lib, self._ctx, self.width, self.height, self.device = lib, C.c_void_p(ctx), width, height, device
+        self.build_stats, self._nrays = None, 0
+
+    def close(self):
+        self._ctx = C.c_void_p()
+
+
+class Group:
+    """One process driving several GPUs (foundation_pt_group_*): the scene is uploaded to every member, `render` renders all tile
+    partitions concurrently and gathers the frame into member 0."""
+
+    def __init__(self, devices, width: int = 1920, height: int = 1080, seed: int = 1, flags: int = 0, background=(0.0, 0.0, 0.0), tile: int = 32,
+                 comm_flags: int = 0, max_leaf_tris: int = 0):
+        self._lib = load_library()
+        cfg = Config(C.sizeof(Config), 0, width, height, seed, max_leaf_tris, flags, (C.c_float * 3)(*background), 0)
+        devs = (C.c_int32 * len(devices))(*devices)
+        self._g = C.c_void_p()
+        st = self._lib.foundation_pt_group_create(C.byref(cfg), devs, len(devices), tile, comm_flags, None, C.byref(self._g))
+        if st != OK:
+            raise FoundationPtError(st, self._lib.foundation_pt_last_error(None).decode())
+        self.members = [_Member(self._lib, self._lib.foundation_pt_group_context(self._g, i), width, height, d) for i, d in enumerate(devices)]
+
+    def load(self, scene: Scene):
+        return [m.load(scene) for m in self.members]
+
+    def render(self, sample_begin: int, sample_count: int, max_bounces: int):
+        st = self._lib.foundation_pt_group_render(self._g, sample_begin, sample_count, max_bounces)
+        if st != OK:
+            raise FoundationPtError(st, self._lib.foundation_pt_group_last_error(self._g).decode())
+
+    def read_accum(self):
+        return self.members[0].read_accum()
+
+    def close(self):
+        if getattr(self, "_g", None) and self._g.value:
+            for m in self.members:
+                m.close()
+            self._lib.foundation_pt_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

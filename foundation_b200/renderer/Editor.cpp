@@ -1,7 +1,9 @@
 // Editor.cpp — headless stand-in for the reference's only caller of the renderer (src/Editor/Editor.cpp:13-44):
 // construct the allocator, the device handle and the Renderer, call Draw() in a loop, report allocator bytes at exit.
 // There is no window on the GPU box, so the loop runs a fixed number of frames and writes the result to disk instead of presenting.
-//   usage: foundation_editor <scene.fpts> <frames> <samples_per_draw> <max_bounces> [accum.raw] [out.ppm] [spin_degrees_per_frame] [out.pfm]
+//   usage: foundation_editor [--gpus N] [--direct] <scene.fpts> <frames> <samples_per_draw> <max_bounces> [accum.raw] [out.ppm] [spin_degrees_per_frame] [out.pfm]
+// --gpus N renders on CUDA devices 0..N-1 of the box (scene replicated, frame tile-partitioned, gathered over NVLink into device 0 inside
+// Draw(); --direct selects the fused peer-store gather), where the reference takes EnumerateDevices()[0] only (src/Editor/Editor.cpp:18).
 // With a spin angle every frame rotates all instances about +Z by frame * angle before drawing, like the reference's per-frame model
 // matrix (src/Renderer/Renderer.cpp:373): TLAS-only rebuild + accumulation restart each Draw().
 #include <atomic>
@@ -49,13 +51,25 @@ CountingAllocator g_Allocator;
 }  // namespace
 
 int main(int argc, char** argv) {
+    int gpus = 1; bool direct = false;
+    {   // strip the options, keep the positional arguments
+        int w = 1;
+        for (int i = 1; i < argc; ++i) {
+            if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
+            else if (!std::strcmp(argv[i], "--direct")) direct = true;
+            else argv[w++] = argv[i];
+        }
+        argc = w;
+        if (gpus < 1) gpus = 1;
+    }
     if (argc < 5) { std::fprintf(stderr, "usage: %s scene.fpts frames samples_per_draw max_bounces [accum.raw] [out.ppm] [spin] [out.pfm]\n", argv[0]); return 2; }
     Renderer::SceneDesc scene; std::string err;
     if (!scene.Load(argv[1], &err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 2; }
     int frames = std::atoi(argv[2]); uint32_t spd = (uint32_t)std::atoi(argv[3]), bounces = (uint32_t)std::atoi(argv[4]);
     {
-        Renderer::DeviceHandle device{0};                       // the reference takes EnumerateDevices()[0] (Editor.cpp:18)
-        Renderer::Renderer renderer(device, g_Allocator.Ptr(), scene, /*seed*/ 7);
+        std::vector<Renderer::DeviceHandle> devices;            // the reference takes EnumerateDevices()[0] (Editor.cpp:18); --gpus N takes the first N
+        for (int d = 0; d < gpus; ++d) devices.push_back(Renderer::DeviceHandle{d});
+        Renderer::Renderer renderer(devices, g_Allocator.Ptr(), scene, /*seed*/ 7, direct);
         renderer.SetQuality(spd, bounces);
         auto t0 = std::chrono::steady_clock::now();
         const double spin = argc > 7 ? std::atof(argv[7]) : 0.0;
@@ -74,6 +88,7 @@ int main(int argc, char** argv) {
         }
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         foundation_pt_build_stats bs = renderer.BuildStats();
+        std::printf("gpus=%u ", renderer.DeviceCount());
         std::printf("frames=%d spp=%u ms=%.3f spp_per_s=%.2f tris=%llu nodes8=%llu build_ms=%.2f\n", frames, renderer.SamplesDone(), ms,
                     renderer.SamplesDone() / (ms * 1e-3), (unsigned long long)bs.num_triangles, (unsigned long long)bs.num_nodes8, bs.build_ms);
         if (argc > 5) {   // the float4 accumulation buffer as is: radiance sum in rgb, sample count in alpha

@@ -30,38 +30,56 @@ void Renderer::Check(int32_t status, const char* what) const {
 }
 
 Renderer::Renderer(DeviceHandle device, Core::Allocator* allocator, const SceneDesc& scene, uint64_t seed)
-    : m_allocator(allocator), m_device(device), m_width(scene.width), m_height(scene.height) {
+    : Renderer(std::vector<DeviceHandle>{device}, allocator, scene, seed, false) {}
+
+template <class F> void Renderer::ForEachMember(F f) {
+    for (uint32_t i = 0; i < foundation_pt_group_size(m_group); ++i) f(foundation_pt_group_context(m_group, i));
+}
+
+Renderer::Renderer(const std::vector<DeviceHandle>& devices, Core::Allocator* allocator, const SceneDesc& scene, uint64_t seed, bool direct_gather)
+    : m_allocator(allocator), m_device(devices.empty() ? DeviceHandle{} : devices[0]), m_width(scene.width), m_height(scene.height) {
     FOUNDATION_CHECK(allocator != nullptr);
+    FOUNDATION_CHECK(!devices.empty());
     foundation_pt_config cfg;
     std::memset(&cfg, 0, sizeof cfg);
-    cfg.struct_size = sizeof cfg; cfg.device = device.cuda_ordinal; cfg.width = scene.width; cfg.height = scene.height; cfg.seed = seed;
+    cfg.struct_size = sizeof cfg; cfg.width = scene.width; cfg.height = scene.height; cfg.seed = seed;
     std::memcpy(cfg.background, scene.background, sizeof cfg.background);
     foundation_pt_allocator cb{allocator, &AllocCb, &FreeCb};
-    Check(foundation_pt_create(&cfg, &cb, &m_ctx), "foundation_pt_create");
-    // one-time blocking uploads: the analogue of the staging copies at src/Renderer/Renderer.cpp:133-197
-    if (!scene.materials.empty()) Check(foundation_pt_materials_set(m_ctx, scene.materials.data(), (uint32_t)scene.materials.size()), "materials_set");
-    for (const MeshDesc& m : scene.meshes) {
-        uint32_t id = 0;
-        Check(foundation_pt_mesh_create(m_ctx, m.positions.data(), 3 * sizeof(float), (uint32_t)(m.positions.size() / 3), m.indices.data(), FOUNDATION_PT_INDEX_U32,
-                                        (uint32_t)(m.indices.size() / 3), m.material_ids.empty() ? nullptr : m.material_ids.data(), &id),
-              "mesh_create");
-    }
-    if (!scene.instances.empty()) Check(foundation_pt_instances_set(m_ctx, scene.instances.data(), (uint32_t)scene.instances.size()), "instances_set");
-    m_build.struct_size = sizeof m_build;
-    Check(foundation_pt_scene_commit(m_ctx, &m_build), "scene_commit");
-    Check(foundation_pt_camera_set(m_ctx, scene.view, scene.proj), "camera_set");
+    std::vector<int32_t> ordinals;
+    for (const DeviceHandle& d : devices) ordinals.push_back(d.cuda_ordinal);
+    int32_t st = foundation_pt_group_create(&cfg, ordinals.data(), (uint32_t)ordinals.size(), 32, direct_gather ? (uint32_t)FOUNDATION_PT_COMM_DIRECT : 0u, &cb, &m_group);
+    if (st != FOUNDATION_PT_OK) std::fprintf(stderr, "[Foundation] foundation_pt_group_create failed (%d): %s\n", st, foundation_pt_last_error(nullptr));
+    FOUNDATION_CHECK(st == FOUNDATION_PT_OK && "foundation_pt_group_create failed");
+    m_ctx = foundation_pt_group_context(m_group, 0);
+    // one-time blocking uploads on every member (the scene is replicated per device): the analogue of the staging copies at
+    // src/Renderer/Renderer.cpp:133-197
+    ForEachMember([&](foundation_pt_context* c) {
+        foundation_pt_context* saved = m_ctx; m_ctx = c;     // Check() reports the failing member's message
+        if (!scene.materials.empty()) Check(foundation_pt_materials_set(c, scene.materials.data(), (uint32_t)scene.materials.size()), "materials_set");
+        for (const MeshDesc& m : scene.meshes) {
+            uint32_t id = 0;
+            Check(foundation_pt_mesh_create(c, m.positions.data(), 3 * sizeof(float), (uint32_t)(m.positions.size() / 3), m.indices.data(), FOUNDATION_PT_INDEX_U32,
+                                            (uint32_t)(m.indices.size() / 3), m.material_ids.empty() ? nullptr : m.material_ids.data(), &id),
+                  "mesh_create");
+        }
+        if (!scene.instances.empty()) Check(foundation_pt_instances_set(c, scene.instances.data(), (uint32_t)scene.instances.size()), "instances_set");
+        m_build.struct_size = sizeof m_build;
+        Check(foundation_pt_scene_commit(c, &m_build), "scene_commit");
+        Check(foundation_pt_camera_set(c, scene.view, scene.proj), "camera_set");
+        m_ctx = saved;
+    });
     m_present_image = static_cast<uint8_t*>(m_allocator->Allocate((size_t)m_width * m_height * 4, 16));
     FOUNDATION_CHECK(m_present_image != nullptr);
 }
 
 Renderer::~Renderer() {
-    // like the reference's destructor (Renderer.cpp:402-406) this waits for the device: destroy() synchronises the context's streams
+    // like the reference's destructor (Renderer.cpp:402-406) this waits for the device: destroy() synchronises every member's streams
     if (m_present_image) m_allocator->Deallocate(m_present_image);
-    if (m_ctx) foundation_pt_destroy(m_ctx);
+    if (m_group) foundation_pt_group_destroy(m_group);
 }
 
 void Renderer::SetCamera(const float view[16], const float proj[16]) {
-    Check(foundation_pt_camera_set(m_ctx, view, proj), "camera_set");
+    ForEachMember([&](foundation_pt_context* c) { Check(foundation_pt_camera_set(c, view, proj), "camera_set"); });
     m_samples_done = 0;   // a moved camera restarts the progressive accumulation
 }
 void Renderer::SetQuality(uint32_t samples_per_draw, uint32_t max_bounces) {
@@ -69,13 +87,17 @@ void Renderer::SetQuality(uint32_t samples_per_draw, uint32_t max_bounces) {
 }
 
 void Renderer::SetInstances(const foundation_pt_instance* instances, uint32_t count) {
-    Check(foundation_pt_instances_set(m_ctx, instances, count), "instances_set");
-    Check(foundation_pt_scene_commit(m_ctx, &m_build), "scene_commit");   // TLAS-only: the meshes did not change
+    ForEachMember([&](foundation_pt_context* c) {
+        Check(foundation_pt_instances_set(c, instances, count), "instances_set");
+        Check(foundation_pt_scene_commit(c, &m_build), "scene_commit");   // TLAS-only: the meshes did not change
+    });
     m_samples_done = 0;
 }
 
 void Renderer::Draw() {
-    Check(foundation_pt_render(m_ctx, m_samples_done, m_samples_per_draw, m_max_bounces), "render");
+    int32_t st = foundation_pt_group_render(m_group, m_samples_done, m_samples_per_draw, m_max_bounces);   // all devices render their tiles; frame gathered into device 0
+    if (st != FOUNDATION_PT_OK) std::fprintf(stderr, "[Foundation] group_render failed (%d): %s\n", st, foundation_pt_group_last_error(m_group));
+    FOUNDATION_CHECK(st == FOUNDATION_PT_OK && "foundation_pt_group_render failed");
     m_samples_done += m_samples_per_draw;
     Check(foundation_pt_resolve_rgba8(m_ctx, m_present_image, (size_t)m_width * m_height * 4), "resolve_rgba8");
 }

@@ -62,7 +62,9 @@ struct SceneDesc {
 class Renderer {
     Core::Allocator* m_allocator{nullptr};
     DeviceHandle m_device;
-    foundation_pt_context* m_ctx{nullptr};
+    foundation_pt_group* m_group{nullptr};   // one member per device; the frame is gathered into member 0 inside foundation_pt_group_render
+    foundation_pt_context* m_ctx{nullptr};   // member 0 (borrowed from the group)
+    template <class F> void ForEachMember(F f);
     uint32_t m_width{0}, m_height{0};
     uint32_t m_samples_done{0};
     uint32_t m_samples_per_draw{1}, m_max_bounces{4};
@@ -71,6 +73,11 @@ class Renderer {
 
 public:
     Renderer(DeviceHandle device, Core::Allocator* allocator, const SceneDesc& scene, uint64_t seed = 1);
+    // Several devices of one box (the reference takes EnumerateDevices()[0] only, src/Editor/Editor.cpp:18): the scene is replicated, the
+    // frame is split into interleaved tiles and gathered over NVLink inside Draw().  direct_gather: the accumulate kernels store their
+    // tiles straight into device 0's frame over peer memory (FOUNDATION_PT_COMM_DIRECT) instead of packed ncclSend / ncclRecv.
+    Renderer(const std::vector<DeviceHandle>& devices, Core::Allocator* allocator, const SceneDesc& scene, uint64_t seed = 1, bool direct_gather = false);
+    uint32_t DeviceCount() const { return foundation_pt_group_size(m_group); }
     ~Renderer();
     Renderer(const Renderer&) = delete;
     Renderer& operator=(const Renderer&) = delete;

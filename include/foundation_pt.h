@@ -44,7 +44,8 @@ enum {
     FOUNDATION_PT_ERR_CUDA = -3,       /* a CUDA runtime call failed; text has the cudaError string     */
     FOUNDATION_PT_ERR_OOM = -4,        /* host or device allocation failed                              */
     FOUNDATION_PT_ERR_NO_DEVICE = -5,  /* no CUDA device: there is deliberately NO CPU fallback         */
-    FOUNDATION_PT_ERR_UNSUPPORTED = -6
+    FOUNDATION_PT_ERR_UNSUPPORTED = -6,
+    FOUNDATION_PT_ERR_COMM = -7        /* NCCL missing / failed, or peer memory could not be mapped     */
 };
 
 /* Index formats: values mirror RHIResourceFormat usage at Vulkan/Command.cpp:292-302. */
@@ -132,7 +133,7 @@ typedef struct foundation_pt_stats {
     uint64_t rays_shadow;      /* any-hit rays traced by the last render call */
     float last_ms;             /* device time of the last render/trace call (CUDA events on the context's stream) */
     float trace_ms;            /* device time of the last rays_trace_* call (one traversal kernel)                            */
-    float shade_ms;            /* reserved (0): per-stage times of a render are taken with ncu, see profiles/               */
+    float gather_ms;           /* device time of the last multi-GPU gather on this rank (pack + NCCL send/recv + scatter, or the direct mode's barrier) */
     uint32_t reserved;
     uint64_t total_launches;   /* since create */
     float stage_ms[6];         /* FOUNDATION_PT_FLAG_STAGE_TIMING: device time of the last render per wavefront stage (CUDA events between the
@@ -169,6 +170,51 @@ FOUNDATION_PT_API int32_t foundation_pt_camera_set(foundation_pt_context* ctx, c
  *      the reference is single-device (Editor.cpp:18). ---- */
 FOUNDATION_PT_API int32_t foundation_pt_partition_set(foundation_pt_context* ctx, uint32_t rank, uint32_t count, uint32_t tile_size);
 
+/* ---- multi-GPU frame (stage C1).  The frame is split into interleaved tiles (same rule as partition_set), the
+ *      scene is replicated (every member uploads and commits the same scene: the device build is deterministic), and the owned tiles
+ *      are gathered into ONE member's accumulation buffer over NVLink.  No reference counterpart: the reference is single-device
+ *      (src/Editor/Editor.cpp:18); the slot is still Renderer::Draw (src/Renderer/Renderer.cpp:367-401), which stays one blocking call.
+ *
+ *      Two host shapes, one mechanism:
+ *        one process per GPU   comm_unique_id on one rank -> distribute the 128 bytes by any channel -> comm_init on every rank
+ *                              (collective) -> render ... -> gather (collective);
+ *        one process, N GPUs   group_create(devices[], n) -> per-member scene upload through group_context(i) -> group_render.
+ *      NCCL (libnccl.so.2) is loaded at run time by the first of these calls; a single-GPU host never needs it.
+ *
+ *      Gather modes (flags):
+ *        0                          each rank packs its owned pixels and ncclSend()s them; the root ncclRecv()s and scatters.  At
+ *                                   1080p on 8 GPUs that is 4.1 MB per rank instead of the 33.2 MB zero-padded frame of an all-reduce.
+ *        FOUNDATION_PT_COMM_DIRECT  fused compute + collective: every rank's accumulate kernel stores its finished pixels straight into
+ *                                   rank 0's frame over NVLink peer memory (peer access in a group, CUDA IPC across processes); gather
+ *                                   is then only a 4-byte all-reduce that orders those stores.  root must be 0.
+ *      Either way the gathered frame is bit-identical to the single-GPU frame (tests/test_gpu_multi.py, bench.py
+ *      n_gpu_vs_1_gpu_max_abs_diff). ---- */
+#define FOUNDATION_PT_COMM_ID_BYTES 128
+enum { FOUNDATION_PT_COMM_DIRECT = 1u << 0 };
+FOUNDATION_PT_API int32_t foundation_pt_comm_unique_id(uint8_t* id, size_t size_bytes);
+/* Collective over `count` contexts (one per rank).  Fixes this context's tile partition to (rank, count, tile_size; 0 = 32). */
+FOUNDATION_PT_API int32_t foundation_pt_comm_init(foundation_pt_context* ctx, const uint8_t* id, size_t size_bytes, uint32_t rank, uint32_t count,
+                                                  uint32_t tile_size, uint32_t flags);
+/* Collective.  Afterwards rank `root`'s accumulation buffer holds the whole frame (read_accum / resolve_rgba8 there). */
+FOUNDATION_PT_API int32_t foundation_pt_gather(foundation_pt_context* ctx, uint32_t root);
+
+/* Same-device form: scatters `src`'s owned tiles into `dst`'s frame (two different partitions of the same frame on ONE device) with the
+ * pack / scatter kernels of the NCCL form, a device-to-device copy in place of ncclSend / ncclRecv.  Needs no NCCL. */
+FOUNDATION_PT_API int32_t foundation_pt_gather_local(foundation_pt_context* dst, foundation_pt_context* src);
+
+typedef struct foundation_pt_group foundation_pt_group;
+FOUNDATION_PT_API int32_t foundation_pt_group_create(const foundation_pt_config* config /* .device ignored */, const int32_t* devices, uint32_t count,
+                                                     uint32_t tile_size, uint32_t flags, const foundation_pt_allocator* host_alloc,
+                                                     foundation_pt_group** out_group);
+FOUNDATION_PT_API int32_t foundation_pt_group_destroy(foundation_pt_group* group);
+FOUNDATION_PT_API uint32_t foundation_pt_group_size(const foundation_pt_group* group);
+/* Member i (borrowed): upload the scene / set the camera on every member with the per-context calls.  Member 0 receives the frame. */
+FOUNDATION_PT_API foundation_pt_context* foundation_pt_group_context(foundation_pt_group* group, uint32_t index);
+/* All members render their tiles concurrently (render_async on every stream), the frame is gathered into member 0, then all are
+ * waited for: one blocking call, like Draw(). */
+FOUNDATION_PT_API int32_t foundation_pt_group_render(foundation_pt_group* group, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces);
+FOUNDATION_PT_API const char* foundation_pt_group_last_error(const foundation_pt_group* group);
+
 /* ---- render (reference slot: Renderer::Record's pass body, Renderer.cpp:332-351, driven by Draw :367-401) ----
  * Adds samples [sample_begin, sample_begin + sample_count) of every owned pixel to the accumulation buffer.
  * sample_begin == 0 clears the buffer first. */
@@ -186,8 +232,8 @@ FOUNDATION_PT_API int32_t foundation_pt_read_accum(foundation_pt_context* ctx, f
 FOUNDATION_PT_API int32_t foundation_pt_write_accum(foundation_pt_context* ctx, const float* rgba, size_t size_bytes);
 /* accum / spp, clamped to [0,1], packed R8G8B8A8_UNORM (the reference's swapchain format, Renderer.cpp:40). */
 FOUNDATION_PT_API int32_t foundation_pt_resolve_rgba8(foundation_pt_context* ctx, uint8_t* rgba8, size_t size_bytes);
-/* Device address of the accumulation buffer (width*height float4) for zero-copy hand-off to a collective
- * (torch.distributed / NCCL reduce in foundation_b200.distributed).  Valid until destroy. */
+/* Device address of the accumulation buffer (width*height float4) for zero-copy hand-off to another CUDA consumer in the same
+ * process.  Valid until destroy. */
 FOUNDATION_PT_API int32_t foundation_pt_accum_device_ptr(foundation_pt_context* ctx, void** out_device_ptr, size_t* out_size_bytes);
 
 /* ---- parity / bench interface on explicit ray sets (no reference counterpart) ----

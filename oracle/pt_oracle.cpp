@@ -367,7 +367,9 @@ void commit(Scene& s) {
         s.fnodes = s.tnodes;
         for (auto& m : s.meshes) { s.fnodes.insert(s.fnodes.end(), m.nodes.begin(), m.nodes.end()); s.ftris.insert(s.ftris.end(), m.tris.begin(), m.tris.end()); }
     } else { s.fnodes = s.meshes[0].nodes; s.ftris = s.meshes[0].tris; }
-    s.light_area = pt_lights_finalize(s.lights.data(), (uint32_t)s.lights.size());
+    uint32_t nl = (uint32_t)s.lights.size();
+    s.light_area = pt_lights_finalize(s.lights.data(), &nl);   // drops degenerate emitters (same rule as the product)
+    s.lights.resize(nl);
     float ext = 0;
     for (int k = 0; k < 3; ++k) ext = pt_max(ext, s.wbounds.hi[k] - s.wbounds.lo[k]);
     s.ray_eps = ext * PT_RAY_EPS_REL;

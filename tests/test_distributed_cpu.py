@@ -21,6 +21,14 @@ def test_tiles_partition_the_frame_exactly_once():
     assert max(counts) / min(counts) < 1.06            # load balance of the interleave at 1080p / 8 GPUs
 
 
+def test_packed_index_is_the_scanline_rank_of_an_owned_pixel():
+    """Host model of the root's scatter (k_unpack_gathered): position of pixel (x, y) in its owner's packed block, ragged frames included."""
+    for (W, H, T, N) in [(160, 90, 16, 3), (1920, 1080, 32, 8), (100, 70, 32, 2), (64, 48, 16, 5), (37, 29, 8, 5)]:
+        for r in range(N):
+            ys, xs = np.nonzero(fdist.owned_mask(W, H, r, N, T))
+            assert np.array_equal(fdist.packed_index(xs, ys, r, N, W, H, T), np.arange(len(xs))), (W, H, T, N, r)
+
+
 def test_ray_slices_cover_the_set():
     for n, w in ((1 << 20, 8), (1000, 3), (5, 8)):
         sl = [fdist.ray_slice(n, r, w) for r in range(w)]
