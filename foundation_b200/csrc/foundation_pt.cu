@@ -17,6 +17,16 @@
 #include <vector>
 
 #include "../../include/foundation_pt.h"
+#ifndef PT_COLLAPSE_PERSISTENT
+#define PT_COLLAPSE_PERSISTENT 1   // 1: all collapse levels beyond the top in one cooperative kernel (k_collapse_levels); 0: round 1's per-level kernels + host round trips
+#endif
+#ifndef PT_ONESWEEP
+#define PT_ONESWEEP 0        // 0 (default): histogram + look-back scan + scatter kernel per pass; 1: one-sweep form (one up-front histogram kernel, one
+                             // kernel per pass with per-digit decoupled look-back).  Measured on the 10 M-pair sort, same box (profiles/r02_ab_traversal_build.log):
+                             // one-sweep 1.20 ms vs 1.13 ms.  ncu: the one-sweep pass takes 154 us against 89 + 29 + 20 us for scatter + histogram +
+                             // scan: 10 M keys are only 7 waves of tiles, every tile of the first wave has to walk back over all tiles resident
+                             // with it (batched 8 loads per round trip; 16 was slower), and the ranking — not the extra key read — is what a pass costs.
+#endif
 #ifndef PT_AGGLOMERATIVE
 #define PT_AGGLOMERATIVE 1   // 1: the radix tree is built bottom-up inside the refit (k_refit_agg, k_refit_agg_up); 0: k_karras + k_refit + k_refit_up
 #endif
@@ -115,6 +125,7 @@ struct foundation_pt_context {
     foundation_pt_config cfg{};
     foundation_pt_allocator host_alloc{};
     int device = 0, num_sms = 0, trace_blocks_per_sm = 0 /* 0 = kernel's own: 8 flat, 6 two-level */, fetch_thresh = 24;
+    int collapse_blocks = 0; // grid of the persistent collapse kernel: one resident wave on this device
     int refit_blocks = 0;   // occupancy of the tiled refit kernel on this context's device (queried at the first build)
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // compute, H2D, D2H
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -211,6 +222,23 @@ int32_t scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf
 // A2: radix sort driver. keys/vals end up in (keys_a, vals_a) (8 passes = even number of swaps).
 // ------------------------------------------------------------------------------------------------
 int32_t radix_sort(Ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, DevBuf& hist, DevBuf& chunk_sums) {
+#if PT_ONESWEEP
+    (void)chunk_sums;
+    const uint32_t tiles = (n + PT_OS_TILE - 1) / PT_OS_TILE;
+    if (tiles == 0) return 0;
+    // [8 x 256 digit histograms | 8 tickets (padded to 64 words) | 8 x tiles x 256 status words], zeroed by one memset
+    const size_t words = 8 * 256 + 64 + (size_t)8 * tiles * 256;
+    if (hist.bytes < words * 4) PT_CK(hist.alloc(words * 4));
+    PT_CK(cudaMemsetAsync(hist.p, 0, words * 4, ctx->stream));
+    uint32_t* d_hist = hist.as<uint32_t>(); uint32_t* d_ticket = d_hist + 8 * 256; uint32_t* d_status = d_ticket + 64;
+    PT_LAUNCH(ctx, k_rs_hist_all, grid_for(ctx, n, 256, 8), 256, keys_a, n, d_hist);
+    PT_LAUNCH(ctx, k_rs_hist_scan, 8, 256, d_hist);
+    for (int pass = 0; pass < 8; ++pass) {
+        PT_LAUNCH(ctx, k_rs_onesweep, tiles, PT_OS_THREADS, keys_a, vals_a, keys_b, vals_b, n, 8 * pass, d_hist + 256 * pass, d_status + (size_t)pass * tiles * 256, d_ticket + pass);
+        std::swap(keys_a, keys_b); std::swap(vals_a, vals_b);
+    }
+    return 0;
+#else
     uint32_t tiles = (n + PT_RS_TILE - 1) / PT_RS_TILE;
     if (tiles == 0) return 0;
     if (hist.bytes < (size_t)tiles * 256 * 4) PT_CK(hist.alloc((size_t)tiles * 256 * 4));
@@ -223,6 +251,7 @@ int32_t radix_sort(Ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_
         std::swap(keys_a, keys_b); std::swap(vals_a, vals_b);
     }
     return 0;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -291,6 +320,39 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
         m = st[0]; level_start = st[1]; prim_total = st[2];
         if (st[3]) std::swap(refs_a, refs_b);
     }
+#if PT_COLLAPSE_PERSISTENT
+    if (m > 0) {
+        // every remaining level in one cooperative launch: the grid is one resident wave, levels are separated by a grid barrier and the
+        // level totals never leave the device
+        if (!ctx->collapse_blocks) {
+            int per_sm = 0, coop = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse_levels, PT_CL_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+            if (!coop) return ctx->fail(FOUNDATION_PT_ERR_UNSUPPORTED, "device cannot launch cooperative kernels");
+            ctx->collapse_blocks = per_sm * ctx->num_sms;
+        }
+        const uint32_t cap_level = n / 2 + 256;          // a wide node below the root stands for >= 2 primitives and the nodes of a level are disjoint
+        DevBuf block_sums, barrier;
+        PT_CK(slots.alloc((size_t)cap_level * 32)); PT_CK(n_int.alloc((size_t)cap_level * 4)); PT_CK(n_prim.alloc((size_t)cap_level * 4));
+        PT_CK(block_sums.alloc((size_t)ctx->collapse_blocks * 8)); PT_CK(barrier.alloc(16));
+        PT_CK(cudaMemsetAsync(barrier.p, 0, 16, ctx->stream));
+        PtCollapseArgs ca;
+        ca.b = b; ca.refs_a = refs_a.as<uint32_t>(); ca.refs_b = refs_b.as<uint32_t>(); ca.max_leaf = max_leaf; ca.bp = d_bp; ca.nodes = nodes_tmp.as<PtNode8>();
+        ca.leaf_seq = out->leaf_seq.as<uint32_t>(); ca.state = totals.as<uint32_t>(); ca.slots = slots.as<uint32_t>(); ca.n_int = n_int.as<uint32_t>();
+        ca.n_prim = n_prim.as<uint32_t>(); ca.cap = cap_level; ca.block_sums = block_sums.as<uint32_t>(); ca.barrier = barrier.as<uint32_t>(); ca.node_cap = n;
+        // k_collapse_top left {m, level_start, prim_total, parity} in `totals`; the host swapped refs_a / refs_b to make parity 0
+        uint32_t st0[4] = {m, level_start, prim_total, 0u};
+        PT_CK(cudaMemcpyAsync(totals.p, st0, 16, cudaMemcpyHostToDevice, ctx->stream));
+        void* kargs[] = {&ca};
+        PT_CK(cudaLaunchCooperativeKernel((const void*)k_collapse_levels, dim3((unsigned)ctx->collapse_blocks), dim3(PT_CL_THREADS), kargs, 0, ctx->stream));
+        ctx->call_launches++; ctx->total_launches++;
+        uint32_t st[4];
+        PT_CK(cudaMemcpyAsync(st, totals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        PT_CK(cudaStreamSynchronize(ctx->stream));
+        if (st[3] || st[0]) return ctx->fail(FOUNDATION_PT_ERR_STATE, "BVH8 collapse exceeded node capacity");
+        level_start = st[1]; prim_total = st[2]; m = 0;
+    }
+#else
     size_t cap = 0;
     while (m > 0) {
         if (cap < m) {
@@ -313,6 +375,7 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
         prim_total += tot[1]; level_start = next_start; m = tot[0];
         std::swap(refs_a, refs_b);
     }
+#endif
     if (prim_total != n) return ctx->fail(FOUNDATION_PT_ERR_STATE, "BVH8 collapse lost primitives");
     out->num_nodes = level_start;
     PT_CK(out->nodes.alloc((size_t)level_start * sizeof(PtNode8)));

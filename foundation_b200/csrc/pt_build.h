@@ -123,10 +123,15 @@ PT_HD int pt_plan_children(const PtBvh2& b, uint32_t ref, uint32_t* C) {
     while (sp) {
         uint32_t r = st_ref[--sp], j = st_j[sp];
         if (r >= b.n - 1 || j == 1u) { C[nc++] = r; continue; }
-        uint32_t p = (uint32_t)(b.plan[r] >> (8 * (j - 2))) & 0xffu;
-        if (p & 0x80u) { st_ref[sp] = r; st_j[sp++] = j - 1; continue; }
+        // the plan word and both links of r are fetched TOGETHER (the links are only needed when the plan says "split", but waiting for
+        // the plan word first makes every level of the walk two dependent round trips instead of one)
+        const uint64_t pw = b.plan[r];
+        const uint32_t rl = b.left[r], rr = b.right[r];
+        uint32_t p = (uint32_t)(pw >> (8 * (j - 2))) & 0xffu;
+        while ((p & 0x80u) && j > 2u) { --j; p = (uint32_t)(pw >> (8 * (j - 2))) & 0xffu; }   // "j-1 slots are as cheap": same node, fewer slots — no reload
+        if (p & 0x80u) { C[nc++] = r; continue; }                                            // j == 2 and one slot is as cheap: r stays one child
         uint32_t kk = p & 15u;
-        st_ref[sp] = b.right[r]; st_j[sp++] = j - kk; st_ref[sp] = b.left[r]; st_j[sp++] = kk;
+        st_ref[sp] = rr; st_j[sp++] = j - kk; st_ref[sp] = rl; st_j[sp++] = kk;
     }
     return nc;
 }

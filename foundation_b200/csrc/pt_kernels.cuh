@@ -299,6 +299,162 @@ __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_scatter(const uint64_t* __
 }
 
 // ---------------------------------------------------------------------------------------------------
+// A2, one-sweep form (Adinets & Merrill, "Onesweep: a faster least significant digit radix sort for GPUs", 2022): the digit histograms of
+// ALL eight passes are taken in one up-front read of the keys, and every pass is ONE kernel that reads each (key, value) once and writes
+// it once — the tile's global offsets come from a per-digit decoupled look-back over the preceding tiles' published counts instead of a
+// separate histogram kernel + scan kernel per pass (round 1: 3 kernels and 2 extra key reads per pass, 1.13 ms for 10 M pairs).
+// ---------------------------------------------------------------------------------------------------
+#ifndef PT_OS_KPT
+#define PT_OS_KPT 9            // keys per thread: 2304-key tiles
+#endif
+#ifndef PT_OS_LB
+#define PT_OS_LB 8             // predecessors inspected per look-back round trip
+#endif
+#define PT_OS_THREADS 256
+#define PT_OS_TILE (PT_OS_THREADS * PT_OS_KPT)
+#define PT_OS_FLAG_AGG 0x40000000u
+#define PT_OS_FLAG_INC 0x80000000u
+#define PT_OS_VALUE 0x3fffffffu
+
+// hist[p][d] += number of keys whose digit p equals d.  Sorted-ish input (triangles in mesh order) makes the high digits uniform across a
+// warp: those go through one aggregated atomic per warp, the rest through per-lane shared-memory atomics.
+__global__ void __launch_bounds__(256) k_rs_hist_all(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t h[8][256];
+    for (int p = 0; p < 8; ++p) h[p][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t rounds = (n + pt_gsize() - 1) / pt_gsize();
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t i = r * pt_gsize() + pt_gtid();
+        const bool valid = i < n;
+        const uint64_t k = valid ? keys[i] : 0ull;
+        const uint32_t live = __ballot_sync(PT_FULL, valid);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const uint32_t d = (uint32_t)(k >> (8 * p)) & 255u;
+            const uint32_t d0 = __shfl_sync(PT_FULL, d, __ffs(live | 0x80000000u) - 1);
+            if (live == PT_FULL && __all_sync(PT_FULL, d == d0)) { if (pt_lane() == 0) atomicAdd(&h[p][d0], 32u); }
+            else if (valid) atomicAdd(&h[p][d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int p = 0; p < 8; ++p) { const uint32_t c = h[p][threadIdx.x]; if (c) atomicAdd(&hist[p * 256 + threadIdx.x], c); }
+}
+// one block per pass: counts -> exclusive digit offsets, in place
+__global__ void __launch_bounds__(256) k_rs_hist_scan(uint32_t* hist) {
+    uint32_t total;
+    const uint32_t c = hist[blockIdx.x * 256 + threadIdx.x];
+    hist[blockIdx.x * 256 + threadIdx.x] = pt_block_excl_scan(c, &total);
+}
+
+// One pass.  Tiles take tickets (tile t only ever waits for tiles < t, which are running or done), rank their keys exactly like
+// k_rs_scatter (match_any against per-warp counters), then thread d publishes the tile's count of digit d — flag AGG — walks back over the
+// predecessors' words of digit d until it meets an inclusive prefix, publishes its own inclusive prefix — flag INC — and so knows where
+// the tile's run of digit d starts in the output.  status: tiles x 256 words, zero at launch; *ticket zero at launch.
+__global__ void __launch_bounds__(PT_OS_THREADS) k_rs_onesweep(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
+                                                               uint32_t* __restrict__ vout, uint32_t n, int shift, const uint32_t* __restrict__ digit_base,
+                                                               uint32_t* status, uint32_t* ticket) {
+    __shared__ uint32_t wh[PT_OS_THREADS / 32][256];
+    __shared__ uint32_t dstart[256], goff[256];
+    __shared__ uint64_t sbuf[PT_OS_TILE];
+    __shared__ uint32_t s_tile;
+    uint32_t* svals = reinterpret_cast<uint32_t*>(sbuf);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < PT_OS_THREADS / 32; ++w) wh[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * PT_OS_TILE;
+    const uint32_t n_valid = min((uint32_t)PT_OS_TILE, n - base);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint64_t key[PT_OS_KPT];
+    uint32_t lp[PT_OS_KPT];
+#pragma unroll
+    for (int i = 0; i < PT_OS_KPT; ++i) {
+        const uint32_t j = warp * (32 * PT_OS_KPT) + i * 32 + lane;
+        key[i] = j < n_valid ? __ldcs(kin + base + j) : ~0ull;     // padding sorts to the very end of the tile and is never written
+    }
+#pragma unroll
+    for (int i = 0; i < PT_OS_KPT; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+        const uint32_t peers = __match_any_sync(PT_FULL, d);
+        const uint32_t old = wh[warp][d];
+        __syncwarp();
+        if (lane == (uint32_t)__ffs(peers) - 1u) wh[warp][d] = old + (uint32_t)__popc(peers);
+        __syncwarp();
+        lp[i] = old + (uint32_t)__popc(peers & lt);
+    }
+    __syncthreads();
+    {   // thread `tid` owns digit `tid`
+        uint32_t acc = 0;
+#pragma unroll
+        for (int w = 0; w < PT_OS_THREADS / 32; ++w) { const uint32_t c = wh[w][tid]; wh[w][tid] = acc; acc += c; }
+        // padding keys (~0ull) were counted under their digit 255 (any shift): take them out of the published count
+        const uint32_t pad = (tid == 255u) ? (uint32_t)PT_OS_TILE - n_valid : 0u;
+        const uint32_t cnt = acc - pad;
+        volatile uint32_t* st = status;
+        uint32_t excl = 0;
+        if (tile == 0) st[tid] = PT_OS_FLAG_INC | cnt;
+        else {
+            st[(size_t)tile * 256 + tid] = PT_OS_FLAG_AGG | cnt;
+            // Look-back, PT_OS_LB predecessors per round trip: all tiles of a wave start together, so a tile typically has to walk over
+            // every tile that is resident with it before it meets an inclusive prefix — one dependent L2 read per predecessor made the
+            // first version slower than the three-kernel passes it replaces.  The loads of a batch are independent and issued together.
+            bool found = false;
+            for (uint32_t t = tile; t > 0 && !found;) {
+                uint32_t w[PT_OS_LB];
+#pragma unroll
+                for (int i = 0; i < PT_OS_LB; ++i) w[i] = (uint32_t)i < t ? st[(size_t)(t - 1u - i) * 256 + tid] : PT_OS_FLAG_INC;   // before tile 0: an inclusive prefix of 0
+#pragma unroll
+                for (int i = 0; i < PT_OS_LB; ++i) {
+                    if (found) break;
+                    while ((w[i] & ~PT_OS_VALUE) == 0u) w[i] = st[(size_t)(t - 1u - i) * 256 + tid];
+                    excl += w[i] & PT_OS_VALUE;
+                    found = (w[i] & PT_OS_FLAG_INC) != 0u;
+                }
+                t = t > (uint32_t)PT_OS_LB ? t - PT_OS_LB : 0u;
+            }
+            st[(size_t)tile * 256 + tid] = PT_OS_FLAG_INC | (excl + cnt);
+        }
+        goff[tid] = digit_base[tid] + excl;
+        uint32_t total;
+        dstart[tid] = pt_block_excl_scan(acc, &total);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PT_OS_KPT; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+        lp[i] += dstart[d] + wh[warp][d];
+        sbuf[lp[i]] = key[i];
+    }
+    __syncthreads();
+    uint32_t outpos[PT_OS_KPT];
+#pragma unroll
+    for (int k = 0; k < PT_OS_KPT; ++k) {
+        const uint32_t j = k * PT_OS_THREADS + tid;
+        outpos[k] = 0xffffffffu;
+        if (j < n_valid) {
+            const uint64_t kk = sbuf[j];
+            const uint32_t d = (uint32_t)(kk >> shift) & 255u;
+            outpos[k] = goff[d] + (j - dstart[d]);
+            kout[outpos[k]] = kk;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PT_OS_KPT; ++i) {
+        const uint32_t j = warp * (32 * PT_OS_KPT) + i * 32 + lane;
+        if (j < n_valid) svals[lp[i]] = __ldcs(vin + base + j);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PT_OS_KPT; ++k) {
+        const uint32_t j = k * PT_OS_THREADS + tid;
+        if (j < n_valid) vout[outpos[k]] = svals[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // A3 / A4: Karras emit and bottom-up refit (second arriver proceeds)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_karras(const uint64_t* keys, PtBvh2 b) {
@@ -684,6 +840,225 @@ __global__ void __launch_bounds__(PT_TOP_NODES) k_collapse_top(PtBvh2 b, uint32_
     }
     if (tid == 0) { state[0] = m; state[1] = level_start; state[2] = prim_total; state[3] = parity; }
 }
+// ---------------------------------------------------------------------------------------------------
+// A5, all remaining levels in ONE persistent kernel (round 1: per level a select kernel, two scan kernels, an emit kernel and a host
+// round trip for the level's totals).  The grid is one resident wave (cooperative launch); levels are separated by a grid barrier.
+//   phase 1  every wide node of the level is built by EIGHT lanes (one per child / per slot): lane 0 of the group walks the collapse
+//            plan, then each lane loads one child box, the greedy octant assignment runs as 8 rounds of an 8-lane arg-max (the
+//            thread-per-node form spent ~440 warp instructions per node on it: divergent loops over local-memory arrays), each lane
+//            quantises the child of its slot, and the 80-byte node — everything but child_base / tri_base, which need the level's
+//            prefix sums — leaves through shared memory as coalesced words.  Per node it also records the slot refs and the two counts.
+//   barrier, then every block sums the per-block counts before it: no scan kernel, no host.
+//   phase 2  one thread per node: block scan of the counts inside the block's contiguous segment, patch the two bases, write the next
+//            level's refs and the leaf sequence.
+// Same numbering as the level-synchronous path (nodes of a level in ref order, children contiguous in slot order).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pt_grid_barrier(uint32_t* counter, uint32_t& epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();                                   // cumulative: the block's writes (ordered before by the barrier above) become visible device-wide
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile uint32_t*>(counter) < epoch) {}
+        __threadfence();                                   // acquire side: also drops stale L1 lines of this SM
+    }
+    __syncthreads();
+}
+struct PtCollapseArgs {
+    PtBvh2 b; uint32_t* refs_a; uint32_t* refs_b; uint32_t max_leaf; const PtBuildParams* bp; PtNode8* nodes; uint32_t* leaf_seq;
+    uint32_t* state;        // in: {m, level_start, prim_total, parity} from k_collapse_top; out: {0, num_nodes, prim_total, error}
+    uint32_t* slots; uint32_t* n_int; uint32_t* n_prim; uint32_t cap;   // per-level scratch, cap entries
+    uint32_t* block_sums;   // 2 x gridDim
+    uint32_t* barrier;      // zero at launch
+    uint32_t node_cap;      // capacity of `nodes`
+};
+#define PT_CL_THREADS 128
+__global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArgs a) {
+    __shared__ uint32_t s_C[PT_CL_THREADS / 8][8];
+    __shared__ uint32_t s_nc[PT_CL_THREADS / 8];
+    __shared__ __align__(16) uint32_t s_node[PT_CL_THREADS / 8][20];
+    __shared__ uint32_t s_red[4][PT_CL_THREADS / 32];
+    const PtBvh2& b = a.b;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, grp = tid >> 3, k = tid & 7u, gl = lane & ~7u /* first lane of my group */;
+    const float pad = a.bp->pad;
+    uint32_t m = a.state[0], level_start = a.state[1], prim_total = a.state[2];
+    uint32_t* cur = a.state[3] ? a.refs_b : a.refs_a;
+    uint32_t* nxt = a.state[3] ? a.refs_a : a.refs_b;
+    uint32_t epoch = 0, error = 0;
+    while (m > 0) {
+        if (m > a.cap || (uint64_t)level_start + m > a.node_cap) { error = 1; break; }      // grid-uniform
+        const uint32_t seg = (m + gridDim.x - 1) / gridDim.x;
+        const uint32_t lo = min(m, blockIdx.x * seg), hi = min(m, lo + seg);
+        uint32_t sum_i = 0, sum_p = 0;
+        // ---------------- phase 1
+        for (uint32_t w0 = lo; w0 < hi; w0 += PT_CL_THREADS / 8) {      // block-uniform trip count
+            const uint32_t w = w0 + grp;
+            const bool node_ok = w < hi;
+            uint32_t ref = 0, nc = 0;
+            if (node_ok) ref = __ldcg(cur + w);
+            if (node_ok && k == 0) {
+                uint32_t C[8];
+                int n_c;
+                if (pt_b2_count(b, ref) <= a.max_leaf) { C[0] = ref; n_c = 1; } else n_c = pt_plan_children(b, ref, C);
+                for (int i = 0; i < 8; ++i) s_C[grp][i] = i < n_c ? C[i] : PT_NONE;
+                s_nc[grp] = (uint32_t)n_c;
+            }
+            __syncwarp();
+            if (node_ok) nc = s_nc[grp];
+            const bool child_ok = node_ok && k < nc;
+            const uint32_t cref = child_ok ? s_C[grp][k] : PT_NONE;
+            PtBox nb, cb;
+            nb.lox = nb.loy = nb.loz = nb.hix = nb.hiy = nb.hiz = 0.0f; cb = nb;
+            uint32_t ccnt = 0, cfirst = 0;
+            if (node_ok) nb = b.box[ref];
+            if (child_ok) {
+                cb = b.box[cref];
+                // an internal ref covers >= 2 primitives: with one triangle per leaf slot its count / first position (two more loads) are never needed
+                const bool leaf_ref = cref >= b.n - 1;
+                ccnt = leaf_ref ? 1u : (a.max_leaf > 1u ? pt_b2_count(b, cref) : 2u);
+                cfirst = leaf_ref ? cref - (b.n - 1) : (a.max_leaf > 1u ? b.first[cref] : 0u);
+            }
+            // costs of putting this child into slot s: (+-dx +- dy) +- dz, the same operation order as pt_collapse_select
+            const float cx = (nb.lox + nb.hix) * 0.5f, cy = (nb.loy + nb.hiy) * 0.5f, cz = (nb.loz + nb.hiz) * 0.5f;
+            const float dx = (cb.lox + cb.hix) * 0.5f - cx, dy = (cb.loy + cb.hiy) * 0.5f - cy, dz = (cb.loz + cb.hiz) * 0.5f - cz;
+            float c[8];
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) c[sl] = (((sl & 4) ? dx : -dx) + ((sl & 2) ? dy : -dy)) + ((sl & 1) ? dz : -dz);
+            // greedy assignment: nc rounds; in each the best (child, free slot) pair of the group wins, ties to the smallest (child, slot)
+            uint32_t slot_used = 0; bool done = !child_ok; int kslot = -1;       // kslot: child index that landed in slot `k` (this lane as a SLOT)
+            const uint32_t rounds = __reduce_max_sync(PT_FULL, nc);
+            for (uint32_t it = 0; it < rounds; ++it) {
+                int bs = -1; float bv = 0.0f;
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl)
+                    if (!done && !((slot_used >> sl) & 1u) && (bs < 0 || c[sl] > bv)) { bv = c[sl]; bs = sl; }
+                uint32_t key = bs >= 0 ? (k << 3 | (uint32_t)bs) : 0xffu;                // 0xff: no candidate
+#pragma unroll
+                for (int o = 4; o >= 1; o >>= 1) {
+                    const float ov = __shfl_xor_sync(PT_FULL, bv, o);
+                    const uint32_t ok = __shfl_xor_sync(PT_FULL, key, o);
+                    const bool take = ok != 0xffu && (key == 0xffu || ov > bv || (ov == bv && ok < key));
+                    if (take) { bv = ov; key = ok; }
+                }
+                if (key != 0xffu) {                                                     // group-uniform
+                    const uint32_t wk = key >> 3, ws = key & 7u;
+                    slot_used |= 1u << ws;
+                    if (wk == k) done = true;
+                    if (ws == k) kslot = (int)wk;
+                }
+            }
+            // the child of my slot: fetch its data from the lane that owns it
+            const int src = (int)gl + (kslot >= 0 ? kslot : 0);
+            const uint32_t sref = __shfl_sync(PT_FULL, cref, src), scnt = __shfl_sync(PT_FULL, ccnt, src), sfirst = __shfl_sync(PT_FULL, cfirst, src);
+            PtBox sb;
+            sb.lox = __shfl_sync(PT_FULL, cb.lox, src); sb.loy = __shfl_sync(PT_FULL, cb.loy, src); sb.loz = __shfl_sync(PT_FULL, cb.loz, src);
+            sb.hix = __shfl_sync(PT_FULL, cb.hix, src); sb.hiy = __shfl_sync(PT_FULL, cb.hiy, src); sb.hiz = __shfl_sync(PT_FULL, cb.hiz, src);
+            const bool slot_ok = node_ok && kslot >= 0;
+            const bool is_leaf = slot_ok && scnt <= a.max_leaf;
+            const bool is_int = slot_ok && !is_leaf;
+            const uint32_t imask = (__ballot_sync(PT_FULL, is_int) >> gl) & 0xffu;
+            // triangle offset of my leaf inside the node's block: exclusive prefix of the leaf counts over the lower slots
+            uint32_t incl = is_leaf ? scnt : 0u;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { const uint32_t t = __shfl_up_sync(PT_FULL, incl, o, 8); if (k >= (uint32_t)o) incl += t; }
+            const uint32_t off = incl - (is_leaf ? scnt : 0u);
+            const uint32_t nprim = __shfl_sync(PT_FULL, incl, (int)gl + 7);
+            // quantisation frame of the node (pt_collapse_emit's arithmetic)
+            float p[3] = {nb.lox - pad, nb.loy - pad, nb.loz - pad};
+            float hi3[3] = {nb.hix + pad, nb.hiy + pad, nb.hiz + pad};
+            float inv[3]; uint32_t e[3];
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) { e[ax] = pt_quant_exp(hi3[ax] - p[ax]); inv[ax] = pt_u2f((254u - e[ax]) << 23); }
+            uint32_t q[6] = {255u, 255u, 255u, 0u, 0u, 0u}, meta = 0u;
+            if (slot_ok) {
+                q[0] = pt_quant_lo(sb.lox - pad, p[0], inv[0]); q[3] = pt_quant_hi(sb.hix + pad, p[0], inv[0]);
+                q[1] = pt_quant_lo(sb.loy - pad, p[1], inv[1]); q[4] = pt_quant_hi(sb.hiy + pad, p[1], inv[1]);
+                q[2] = pt_quant_lo(sb.loz - pad, p[2], inv[2]); q[5] = pt_quant_hi(sb.hiz + pad, p[2], inv[2]);
+                meta = is_leaf ? ((((1u << scnt) - 1u) << 5) | off) : (0x20u | (24u + k));
+            }
+            if (node_ok) {
+                uint8_t* img = reinterpret_cast<uint8_t*>(&s_node[grp][0]);
+                img[24 + k] = (uint8_t)meta;
+#pragma unroll
+                for (int pl = 0; pl < 6; ++pl) img[32 + 8 * pl + k] = (uint8_t)q[pl];
+                if (k == 0) {
+                    s_node[grp][0] = pt_f2u(p[0]); s_node[grp][1] = pt_f2u(p[1]); s_node[grp][2] = pt_f2u(p[2]);
+                    s_node[grp][3] = e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24);
+                    s_node[grp][4] = 0u; s_node[grp][5] = 0u;                             // child_base, tri_base: phase 2
+                    a.n_int[w] = (uint32_t)__popc(imask); a.n_prim[w] = nprim;
+                    sum_i += (uint32_t)__popc(imask); sum_p += nprim;
+                }
+                a.slots[8 * (size_t)w + k] = slot_ok ? sref : PT_NONE;
+                // first sorted position of my leaf's primitives rides along in the high part of the scratch: phase 2 needs it without touching first[] again
+            }
+            __syncwarp();
+            {   // the warp's (up to) four nodes leave as consecutive words
+                const uint32_t wfirst = w0 + warp * 4u;
+                const uint32_t nn = wfirst < hi ? min(4u, hi - wfirst) : 0u;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(a.nodes + level_start + wfirst);
+                const uint32_t* srcw = &s_node[warp * 4u][0];
+                for (uint32_t i = lane; i < nn * 20u; i += 32u) dst[i] = srcw[i];
+            }
+            __syncwarp();
+        }
+        // per-block counts of this level
+        sum_i = __reduce_add_sync(PT_FULL, sum_i); sum_p = __reduce_add_sync(PT_FULL, sum_p);
+        if (lane == 0) { s_red[0][warp] = sum_i; s_red[1][warp] = sum_p; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t si = 0, sp = 0;
+            for (int i = 0; i < PT_CL_THREADS / 32; ++i) { si += s_red[0][i]; sp += s_red[1][i]; }
+            a.block_sums[2 * blockIdx.x] = si; a.block_sums[2 * blockIdx.x + 1] = sp;
+        }
+        pt_grid_barrier(a.barrier, epoch);
+        // ---------------- offsets of this block's segment + the level's totals
+        uint32_t pre_i = 0, pre_p = 0, tot_i = 0, tot_p = 0;
+        for (uint32_t bb = tid; bb < gridDim.x; bb += PT_CL_THREADS) {
+            const uint32_t vi = __ldcg(a.block_sums + 2 * bb), vp = __ldcg(a.block_sums + 2 * bb + 1);
+            tot_i += vi; tot_p += vp;
+            if (bb < blockIdx.x) { pre_i += vi; pre_p += vp; }
+        }
+        pre_i = __reduce_add_sync(PT_FULL, pre_i); pre_p = __reduce_add_sync(PT_FULL, pre_p);
+        tot_i = __reduce_add_sync(PT_FULL, tot_i); tot_p = __reduce_add_sync(PT_FULL, tot_p);
+        if (lane == 0) { s_red[0][warp] = pre_i; s_red[1][warp] = pre_p; s_red[2][warp] = tot_i; s_red[3][warp] = tot_p; }
+        __syncthreads();
+        pre_i = pre_p = tot_i = tot_p = 0;
+        for (int i = 0; i < PT_CL_THREADS / 32; ++i) { pre_i += s_red[0][i]; pre_p += s_red[1][i]; tot_i += s_red[2][i]; tot_p += s_red[3][i]; }
+        __syncthreads();
+        // ---------------- phase 2
+        const uint32_t next_start = level_start + m;
+        for (uint32_t w0 = lo; w0 < hi; w0 += PT_CL_THREADS) {
+            const uint32_t w = w0 + tid;
+            const bool ok = w < hi;
+            const uint32_t ni = ok ? a.n_int[w] : 0u, np = ok ? a.n_prim[w] : 0u;
+            uint32_t ti, tp;
+            const uint32_t oi = pre_i + pt_block_excl_scan(ni, &ti);
+            const uint32_t op = pre_p + pt_block_excl_scan(np, &tp);
+            pre_i += ti; pre_p += tp;
+            if (ok) {
+                const uint32_t child_base = next_start + oi, prim_base = prim_total + op;
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(a.nodes + level_start + w) + 4) = make_uint2(child_base, prim_base);
+                uint32_t offp = 0, nint = 0;
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl) {
+                    const uint32_t r = a.slots[8 * (size_t)w + sl];
+                    if (r == PT_NONE) continue;
+                    const uint32_t cnt = r >= b.n - 1 ? 1u : (a.max_leaf > 1u ? pt_b2_count(b, r) : 2u);   // an internal ref covers >= 2 primitives
+                    if (cnt <= a.max_leaf) {
+                        const uint32_t fp = pt_b2_lopos(b, r);
+                        for (uint32_t qq = 0; qq < cnt; ++qq) a.leaf_seq[prim_base + offp + qq] = fp + qq;
+                        offp += cnt;
+                    } else nxt[oi + nint++] = r;
+                }
+            }
+        }
+        pt_grid_barrier(a.barrier, epoch);
+        level_start = next_start; prim_total += tot_p; m = tot_i;
+        uint32_t* t = cur; cur = nxt; nxt = t;
+    }
+    if (blockIdx.x == 0 && tid == 0) { a.state[0] = m; a.state[1] = level_start; a.state[2] = prim_total; a.state[3] = error; }
+}
+
 __global__ void __launch_bounds__(256) k_write_tris(PtMeshRaw m, const uint32_t* order, const uint32_t* leaf_seq, PtTri* tris) {
     for (uint32_t k = pt_gtid(); k < m.ntris; k += pt_gsize()) {
         uint32_t i = order[leaf_seq[k]];
@@ -801,7 +1176,7 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
         if (!__any_sync(PT_FULL, active)) break;
         while (active) {
             if (pt_trav_step<ANY, TWO_LEVEL>(sc, &st, stack, &best, cnt) == PT_STEP_DONE) {
-                if (st.overflow) atomicOr(status, 1u);
+                if (st.sp < 0) atomicOr(status, 1u);       // traversal-stack overflow (pt_trav_step left sp = -1)
                 job.store(idx, best);
                 active = false;
                 break;

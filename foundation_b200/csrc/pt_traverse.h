@@ -71,6 +71,22 @@ PT_HD float pt_qfloat(uint32_t w, int i, uint32_t qbias) { return __uint_as_floa
 PT_HD float pt_qfloat(uint32_t w, int i, uint32_t qbias) { return pt_u2f(qbias | (pt_byte(w, i) << 8)); }
 #endif
 
+#ifndef PT_NODE_F32X2
+#define PT_NODE_F32X2 1      // 24 FFMA2 instead of 48 FFMA per node test.  Same-box A/B (profiles/r02_ab_traversal_build.log): +1.9 % spp/s, +2.5 % any-hit,
+                             // -1 % on the closest-hit ray sets: the node test is bound by the ALU pipe (PRMT / FMNMX / LOP3) and by load latency, not by the fma pipe
+#endif
+#if defined(__CUDA_ARCH__)
+// {lo, hi} = {q0 * a0 + c0, q1 * a1 + c1} in ONE instruction (fma.rn.f32x2, sm_100+)
+__device__ __forceinline__ void pt_fma2(float q0, float q1, float a0, float a1, float c0, float c1, float* lo, float* hi) {
+    unsigned long long q, m, c, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(q0), "f"(q1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(m) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(q), "l"(m), "l"(c));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(*lo), "=f"(*hi) : "l"(r));
+}
+#endif
+
 // Intersects the 8 quantised child boxes of one node.  Returns the hit mask: bits 24..31 = internal
 // children that are hit, at position 24 + (slot ^ oct_inv); bits 0..23 = triangles of leaf slots that are hit.
 PT_HD uint32_t pt_node_hits(const PtU4& n0, const PtU4& n1, const PtU4& n2, const PtU4& n3, const PtU4& n4, const PtRayCtx& r, float tmin,
@@ -107,9 +123,19 @@ PT_HD uint32_t pt_node_hits(const PtU4& n0, const PtU4& n1, const PtU4& n2, cons
 #pragma unroll
 #endif
         for (int j = 0; j < 4; ++j) {
+#if defined(__CUDA_ARCH__) && PT_NODE_F32X2
+            // sm_100 packed fp32 (FFMA2): {near x, near y} and {far x, far y} share the multiplier pair {ax, ay}, {near z, far z} the pair
+            // {az, az} — four multiplier registers instead of three (pairing near / far on every axis needs six and spills at the
+            // 64-register cap).  Each half is an IEEE round-to-nearest fma of its own operands: the same bits as the scalar fmas (and the oracle's).
+            float tnx, tfx, tny, tfy, tnz, tfz;
+            pt_fma2(pt_qfloat(nx, j, qbias), pt_qfloat(ny, j, qbias), ax, ay, bnx, bny, &tnx, &tny);
+            pt_fma2(pt_qfloat(fx, j, qbias), pt_qfloat(fy, j, qbias), ax, ay, bfx, bfy, &tfx, &tfy);
+            pt_fma2(pt_qfloat(nz, j, qbias), pt_qfloat(fz, j, qbias), az, az, bnz, bfz, &tnz, &tfz);
+#else
             float tnx = pt_fma(pt_qfloat(nx, j, qbias), ax, bnx), tfx = pt_fma(pt_qfloat(fx, j, qbias), ax, bfx);
             float tny = pt_fma(pt_qfloat(ny, j, qbias), ay, bny), tfy = pt_fma(pt_qfloat(fy, j, qbias), ay, bfy);
             float tnz = pt_fma(pt_qfloat(nz, j, qbias), az, bnz), tfz = pt_fma(pt_qfloat(fz, j, qbias), az, bfz);
+#endif
             float tn = pt_fmax(pt_fmax(tnx, tny), pt_fmax(tnz, tmin));
             float tf = pt_fmin(pt_fmin(tfx, tfy), pt_fmin(tfz, tbest));
             uint32_t sel = (tn <= tf) ? 0xffffffffu : 0u;
@@ -168,8 +194,8 @@ struct PtTravState {
     float tmin;
     PtU2 ng, tg;
     uint32_t node_base, tri_base, cur_inst, cur_iidx;
-    int sp;
-    bool in_blas, overflow;
+    int sp;            // stack entries in use; -1 after a stack overflow (the ray is abandoned, the kernels report it through the status word)
+    bool in_blas;
 };   // the group stack is a separate array so this struct stays in registers
 enum { PT_STEP_RUNNING = 0, PT_STEP_DONE = 1 };
 
@@ -180,7 +206,7 @@ PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax
     pt_ray_ctx(&s->world, o, d);
     s->r = s->world;
     s->tmin = tmin;
-    s->sp = 0; s->overflow = false;
+    s->sp = 0;
     s->in_blas = !TWO_LEVEL;
     s->node_base = TWO_LEVEL ? tlas_base : 0u; s->tri_base = 0; s->cur_inst = TWO_LEVEL ? PT_NONE : 0u; s->cur_iidx = 0;
     // root: one pending child of a virtual parent with child_base 0 and an empty imask, so popc(...) = 0 -> node 0
@@ -225,7 +251,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, Stack& stack, PtHi
         child = s->ng.x + (uint32_t)pt_popc(s->ng.y & 0xffu & ~(0xffffffffu << slot));
         nbase = s->node_base;
         if (s->ng.y & 0xff000000u) {
-            if (s->sp >= PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
+            if (s->sp >= PT_STACK_SIZE) { s->sp = -1; return PT_STEP_DONE; }
             stack.put(s->sp++, s->ng);
         }
     }
@@ -237,7 +263,7 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, Stack& stack, PtHi
             if (ANY && best->prim != PT_NONE) return PT_STEP_DONE;
         } else {
             // TLAS leaf: enter the instance.  Save the remaining groups, push the return sentinel.
-            if (s->sp + 3 > PT_STACK_SIZE) { s->overflow = true; return PT_STEP_DONE; }
+            if (s->sp + 3 > PT_STACK_SIZE) { s->sp = -1; return PT_STEP_DONE; }
             if (s->ng.y & 0xff000000u) stack.put(s->sp++, s->ng);   // popped last: the node's remaining instances come before its internal children
             if (s->tg.y) stack.put(s->sp++, s->tg);
             PtU2 sentinel; sentinel.x = PT_NONE; sentinel.y = 0; stack.put(s->sp++, sentinel);
@@ -279,5 +305,5 @@ PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, floa
     PtArrayStack stack;
     pt_trav_init<TWO_LEVEL>(&s, o, d, tmin, tmax, best, sc.tlas_base);
     while (pt_trav_step<ANY, TWO_LEVEL>(sc, &s, stack, best, cnt) == PT_STEP_RUNNING) {}
-    return !s.overflow;
+    return s.sp >= 0;
 }
