@@ -149,7 +149,9 @@ def run_reference(a, rank, world):
     dt = time.perf_counter() - t0
     v = n * a.steps / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(a, world), reference_arm_rays_per_step=n,
+                           reference_arm_note=f"bounded sample: the CPU arm traces the first 2^{int(np.log2(n))} rays of the same set per step (a rate, comparable per ray)"),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"first 2^{int(np.log2(n))} rays of the seed-4 incoherent set per step, CPU oracle BVH traversal, {cores} threads"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -305,7 +307,7 @@ def main():
         hit_mask = gh_resident["prim"] != 0xFFFFFFFF
         extra["hit_fraction"] = float(hit_mask.mean())
         sets = {"hits_only": rays[hit_mask]}
-        cam = scenes.camera_rays(sc, 1 << 23, 3)
+        cam = scenes.camera_rays(sc, 1 << max(16, min(23, a.log2_rays - 3)), 3)
         ch, _ = tr.trace_closest(cam)
         extra["primary_hit_fraction"] = float((ch["prim"] != 0xFFFFFFFF).mean())
         sets["secondary"] = scenes.secondary_rays(sc, cam, ch)
@@ -314,7 +316,7 @@ def main():
             tr.rays_upload(rs)
             ms, _ = time_resident(5, 2)
             extra[name] = {"rays": int(len(rs)), "mrays_per_s": len(rs) * 5 / (ms * 1e-3) / 1e6, "kernel_ms": ms / 5, "_rays": rs}
-        extra["secondary"]["what"] = ("bounce rays regenerated on the host from 2^23 primary camera hits of this scene: origin on the surface, "
+        extra["secondary"]["what"] = ("bounce rays regenerated on the host from the primary camera hits (2^23 camera rays at full size) of this scene: origin on the surface, "
                                       "cosine-weighted direction (the Lambert lobe of the render at bounce 1)")
         tr.rays_upload(rays)
     if world > 1:

@@ -103,6 +103,7 @@ struct Mesh {
     Mesh(Mesh&&) = default; Mesh& operator=(Mesh&&) = default;
     uint32_t stride = 0, idx_fmt = 0, nverts = 0, ntris = 0;
     DevBuf d_pos, d_idx, d_mat;
+    DevBuf d_uv, d_col;      // optional per-vertex attributes, tightly packed (float2 / float3)
     // build products
     DevBuf d_nodes, d_tris, d_order;
     uint32_t num_nodes = 0;
@@ -151,6 +152,13 @@ struct foundation_pt_context {
     foundation_pt_build_stats bstats{};
 
     PtCamera cam{}; bool cam_set = false;
+
+    // vertex attributes + albedo textures (the reference's material inputs: vertex colour, uv, one RGBA8 texture)
+    struct Texture { DevBuf texels; uint32_t width = 0, height = 0; };
+    std::vector<Texture> textures;
+    std::vector<uint32_t> mat_tex;                       // per material: texture id or PT_NONE
+    DevBuf d_mesh_attr, d_textures, d_mat_tex, w_hit_uv;
+    bool attr_enabled = false;
 
     // wavefront state
     uint32_t part_rank = 0, part_count = 1, part_tile = 32;
@@ -494,6 +502,7 @@ int32_t setup_wave(Ctx* ctx) {
     PT_CK(ctx->w_ray_o.alloc(S * 16)); PT_CK(ctx->w_ray_d.alloc(S * 16)); PT_CK(ctx->w_beta.alloc(S * 16)); PT_CK(ctx->w_L.alloc(S * 16));
     PT_CK(ctx->w_rng.alloc(S * 16)); PT_CK(ctx->w_hit.alloc(S * 16)); PT_CK(ctx->w_active.alloc(S * 4)); PT_CK(ctx->w_next.alloc(S * 4));
     PT_CK(ctx->w_sorted.alloc(S * 4)); PT_CK(ctx->w_sh_o.alloc(S * 16)); PT_CK(ctx->w_sh_d.alloc(S * 16)); PT_CK(ctx->w_sh_c.alloc(S * 16));
+    if (ctx->attr_enabled) PT_CK(ctx->w_hit_uv.alloc(S * 8)); else ctx->w_hit_uv.release();
     PT_CK(ctx->w_ctr.alloc(sizeof(PtWaveCounters))); PT_CK(ctx->w_keyhist.alloc((PT_KEY_BUCKETS + 1) * 4));
     PT_CK(cudaMemsetAsync(ctx->w_ctr.p, 0, sizeof(PtWaveCounters), ctx->stream));
     if (!ctx->d_accum.p) {
@@ -514,6 +523,8 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
     w.ctr = ctx->w_ctr.as<PtWaveCounters>(); w.key_hist = ctx->w_keyhist.as<uint32_t>(); w.num_slots = ctx->num_slots; w.num_pixels = ctx->num_slots;
     PtShadeScene ss;
     ss.sv = ctx->view; ss.mats = ctx->d_mats.as<PtMaterial>(); ss.num_mats = (uint32_t)ctx->mats.size();
+    ss.mesh_attr = ctx->attr_enabled ? ctx->d_mesh_attr.as<PtMeshAttr>() : nullptr; ss.textures = ctx->d_textures.as<PtTexture>(); ss.mat_tex = ctx->d_mat_tex.as<uint32_t>();
+    w.hit_uv = ctx->attr_enabled ? ctx->w_hit_uv.as<float2>() : nullptr;
     ss.sc.lights = ctx->d_lights.as<PtLight>(); ss.sc.num_lights = ctx->num_lights; ss.sc.light_area = ctx->light_area; ss.sc.ray_eps = ctx->ray_eps;
     ss.sc.flags = ctx->cfg.flags; ss.sc.seed = ctx->cfg.seed; ss.sc.max_bounces = max_bounces;
     ss.sc.bg[0] = ctx->cfg.background[0]; ss.sc.bg[1] = ctx->cfg.background[1]; ss.sc.bg[2] = ctx->cfg.background[2];
@@ -853,6 +864,68 @@ int32_t foundation_pt_instances_set(foundation_pt_context* ctx, const foundation
     PT_CATCH(ctx)
 }
 
+int32_t foundation_pt_mesh_attributes_set(foundation_pt_context* ctx, uint32_t mesh_id, const void* uv, size_t uv_stride_bytes, const void* color, size_t color_stride_bytes) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
+    if (mesh_id >= ctx->meshes.size()) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_attributes_set: mesh_id out of range");
+    if ((uv && (uv_stride_bytes < 8 || (uv_stride_bytes & 3))) || (color && (color_stride_bytes < 12 || (color_stride_bytes & 3))))
+        return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "mesh_attributes_set: strides must be multiples of 4, >= 8 (uv) / >= 12 (colour)");
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    Mesh& m = ctx->meshes[mesh_id];
+    // the streams are compacted on the way in (float2 / float3 per vertex): the caller's layout — e.g. the reference's interleaved,
+    // over-aligned vertex_input (Renderer.cpp:23-27) — ends at this call
+    HostVec<float> tmp{CbAlloc<float>(ctx->host_alloc.alloc ? &ctx->host_alloc : nullptr)};
+    auto upload = [&](const void* src, size_t stride, int comps, DevBuf& dst) -> int32_t {
+        if (!src) { dst.release(); return 0; }
+        tmp.resize((size_t)m.nverts * comps);
+        for (uint32_t v = 0; v < m.nverts; ++v) memcpy(&tmp[(size_t)v * comps], (const uint8_t*)src + (size_t)v * stride, 4 * (size_t)comps);
+        PT_CK(dst.alloc(tmp.size() * 4));
+        PT_CK(cudaMemcpyAsync(dst.p, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        PT_CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    int32_t rc = upload(uv, uv_stride_bytes, 2, m.d_uv);
+    if (!rc) rc = upload(color, color_stride_bytes, 3, m.d_col);
+    if (rc) return rc;
+    ctx->committed = false;
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_texture_create(foundation_pt_context* ctx, const void* rgba8, uint32_t width, uint32_t height, size_t row_pitch_bytes, uint32_t* out_texture_id) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
+    if (!rgba8 || width == 0 || height == 0 || width > 32768 || height > 32768) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "texture_create: bad image");
+    if (row_pitch_bytes == 0) row_pitch_bytes = (size_t)width * 4;
+    if (row_pitch_bytes < (size_t)width * 4) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "texture_create: row pitch smaller than a row");
+    PT_TRY
+    cudaSetDevice(ctx->device);
+    foundation_pt_context::Texture t;
+    t.width = width; t.height = height;
+    PT_CK(t.texels.alloc((size_t)width * height * 4));
+    PT_CK(cudaMemcpy2DAsync(t.texels.p, (size_t)width * 4, rgba8, row_pitch_bytes, (size_t)width * 4, height, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    ctx->textures.push_back(std::move(t));
+    if (out_texture_id) *out_texture_id = (uint32_t)ctx->textures.size() - 1;
+    ctx->committed = false;
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
+int32_t foundation_pt_material_textures_set(foundation_pt_context* ctx, const uint32_t* texture_ids, uint32_t count) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    settle(ctx);
+    if (!texture_ids && count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "material_textures_set: NULL ids");
+    PT_TRY
+    for (uint32_t i = 0; i < count; ++i)
+        if (texture_ids[i] != FOUNDATION_PT_NO_TEXTURE && texture_ids[i] >= ctx->textures.size()) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "material_textures_set: texture id out of range");
+    ctx->mat_tex.assign(texture_ids, texture_ids + count);
+    ctx->committed = false;
+    return FOUNDATION_PT_OK;
+    PT_CATCH(ctx)
+}
+
 int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_build_stats* stats) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
     settle(ctx);
@@ -1008,6 +1081,29 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
     if (!lights.empty()) PT_CK(cudaMemcpyAsync(ctx->d_lights.p, lights.data(), lights.size() * sizeof(PtLight), cudaMemcpyHostToDevice, ctx->stream));
     PT_CK(ctx->d_mats.alloc(ctx->mats.size() * sizeof(PtMaterial)));
     PT_CK(cudaMemcpyAsync(ctx->d_mats.p, ctx->mats.data(), ctx->mats.size() * sizeof(PtMaterial), cudaMemcpyHostToDevice, ctx->stream));
+    {   // attribute tables: per mesh {uv, colour, indices}, the texture descriptors, the per-material texture ids
+        bool any = false;
+        std::vector<PtMeshAttr> ma(ctx->meshes.size());
+        for (size_t k = 0; k < ctx->meshes.size(); ++k) {
+            const Mesh& m = ctx->meshes[k];
+            ma[k].uv = m.d_uv.as<uint8_t>(); ma[k].col = m.d_col.as<uint8_t>(); ma[k].idx = m.d_idx.p; ma[k].uv_stride = 8; ma[k].col_stride = 12; ma[k].idx_fmt = m.idx_fmt; ma[k].pad = 0;
+            any |= m.d_uv.p != nullptr || m.d_col.p != nullptr;
+        }
+        const bool was = ctx->attr_enabled;
+        ctx->attr_enabled = any;
+        if (any != was) ctx->wave_ready = false;                  // the wavefront state grows / loses the per-slot barycentrics
+        if (any) {
+            std::vector<PtTexture> td(ctx->textures.size() ? ctx->textures.size() : 1);
+            for (size_t k = 0; k < ctx->textures.size(); ++k) { td[k].texels = ctx->textures[k].texels.as<uint32_t>(); td[k].width = ctx->textures[k].width; td[k].height = ctx->textures[k].height; td[k].pad = 0; }
+            std::vector<uint32_t> mt(ctx->mats.size(), PT_NONE);
+            for (size_t k = 0; k < mt.size() && k < ctx->mat_tex.size(); ++k) mt[k] = ctx->mat_tex[k] < ctx->textures.size() ? ctx->mat_tex[k] : PT_NONE;
+            PT_CK(ctx->d_mesh_attr.alloc(ma.size() * sizeof(PtMeshAttr))); PT_CK(ctx->d_textures.alloc(td.size() * sizeof(PtTexture))); PT_CK(ctx->d_mat_tex.alloc(mt.size() * 4));
+            PT_CK(cudaMemcpyAsync(ctx->d_mesh_attr.p, ma.data(), ma.size() * sizeof(PtMeshAttr), cudaMemcpyHostToDevice, ctx->stream));
+            PT_CK(cudaMemcpyAsync(ctx->d_textures.p, td.data(), td.size() * sizeof(PtTexture), cudaMemcpyHostToDevice, ctx->stream));
+            PT_CK(cudaMemcpyAsync(ctx->d_mat_tex.p, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            PT_CK(cudaStreamSynchronize(ctx->stream));           // ma / td / mt are locals
+        }
+    }
     float ext = 0;
     for (int k = 0; k < 3; ++k) ext = pt_max(ext, ctx->whi[k] - ctx->wlo[k]);
     ctx->ray_eps = ext * PT_RAY_EPS_REL;
@@ -1223,11 +1319,11 @@ int32_t foundation_pt_rays_download_hits(foundation_pt_context* ctx, uint64_t fi
 }
 
 // Host-buffer variants: H2D + kernel + D2H inside the call, chunked so copies of one chunk overlap the
-// traversal of another when the caller's buffers are pinned.
-int32_t foundation_pt_trace_closest(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count, foundation_pt_hit* out_hits, uint32_t* out_inst) {
-    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
-    if ((!rays || !out_hits) && count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "trace_closest: NULL buffer");
-    if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "trace: scene not committed");
+// traversal of another when the caller's buffers are pinned (closest-hit and any-hit share the pipeline).
+}  // extern "C"
+namespace {
+template <bool ANY>
+int32_t trace_host_pipelined(Ctx* ctx, const foundation_pt_ray* rays, uint64_t count, foundation_pt_hit* out_hits, uint32_t* out_inst, uint8_t* out_occ) {
     PT_TRY
     cudaSetDevice(ctx->device);
     if (ctx->d_rays.bytes < count * 32) {
@@ -1242,12 +1338,16 @@ int32_t foundation_pt_trace_closest(foundation_pt_context* ctx, const foundation
         PT_CK(cudaMemcpyAsync(ctx->d_rays.as<uint8_t>() + b * 32, rays + b, n * 32, cudaMemcpyHostToDevice, ctx->stream2));
         PT_CK(cudaEventRecord(done_h2d, ctx->stream2));
         PT_CK(cudaStreamWaitEvent(ctx->stream, done_h2d, 0));
-        int32_t rc = launch_trace<false>(ctx, ctx->d_rays.as<float4>() + 2 * b, n, ctx->d_hits.as<float4>() + b, ctx->d_hit_inst.as<uint32_t>() + b, nullptr);
+        int32_t rc = ANY ? launch_trace<true>(ctx, ctx->d_rays.as<float4>() + 2 * b, n, nullptr, nullptr, ctx->d_occ.as<uint8_t>() + b)
+                         : launch_trace<false>(ctx, ctx->d_rays.as<float4>() + 2 * b, n, ctx->d_hits.as<float4>() + b, ctx->d_hit_inst.as<uint32_t>() + b, nullptr);
         if (rc) return rc;
         PT_CK(cudaEventRecord(done_k, ctx->stream));
         PT_CK(cudaStreamWaitEvent(ctx->stream3, done_k, 0));
-        PT_CK(cudaMemcpyAsync(out_hits + b, ctx->d_hits.as<float4>() + b, n * 16, cudaMemcpyDeviceToHost, ctx->stream3));
-        if (out_inst) PT_CK(cudaMemcpyAsync(out_inst + b, ctx->d_hit_inst.as<uint32_t>() + b, n * 4, cudaMemcpyDeviceToHost, ctx->stream3));
+        if (ANY) PT_CK(cudaMemcpyAsync(out_occ + b, ctx->d_occ.as<uint8_t>() + b, n, cudaMemcpyDeviceToHost, ctx->stream3));
+        else {
+            PT_CK(cudaMemcpyAsync(out_hits + b, ctx->d_hits.as<float4>() + b, n * 16, cudaMemcpyDeviceToHost, ctx->stream3));
+            if (out_inst) PT_CK(cudaMemcpyAsync(out_inst + b, ctx->d_hit_inst.as<uint32_t>() + b, n * 4, cudaMemcpyDeviceToHost, ctx->stream3));
+        }
     }
     PT_CK(cudaStreamSynchronize(ctx->stream2));
     PT_CK(cudaStreamSynchronize(ctx->stream3));
@@ -1256,17 +1356,21 @@ int32_t foundation_pt_trace_closest(foundation_pt_context* ctx, const foundation
     return check_status(ctx);
     PT_CATCH(ctx)
 }
+}  // namespace
+extern "C" {
+
+int32_t foundation_pt_trace_closest(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count, foundation_pt_hit* out_hits, uint32_t* out_inst) {
+    if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
+    if ((!rays || !out_hits) && count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "trace_closest: NULL buffer");
+    if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "trace: scene not committed");
+    return trace_host_pipelined<false>(ctx, rays, count, out_hits, out_inst, nullptr);
+}
 
 int32_t foundation_pt_trace_any(foundation_pt_context* ctx, const foundation_pt_ray* rays, uint64_t count, uint8_t* out_occluded) {
     if (!ctx) return FOUNDATION_PT_ERR_ARGUMENT;
     if ((!rays || !out_occluded) && count) return ctx->fail(FOUNDATION_PT_ERR_ARGUMENT, "trace_any: NULL buffer");
-    int32_t rc = foundation_pt_rays_upload(ctx, rays, count);
-    if (rc) return rc;
-    rc = foundation_pt_rays_trace_any(ctx, 0, count);
-    if (rc) return rc;
-    cudaSetDevice(ctx->device);
-    if (count) PT_CK(cudaMemcpy(out_occluded, ctx->d_occ.p, count, cudaMemcpyDeviceToHost));
-    return FOUNDATION_PT_OK;
+    if (!ctx->committed) return ctx->fail(FOUNDATION_PT_ERR_STATE, "trace: scene not committed");
+    return trace_host_pipelined<true>(ctx, rays, count, nullptr, nullptr, out_occluded);
 }
 
 int32_t foundation_pt_stats_get(foundation_pt_context* ctx, foundation_pt_stats* stats) {

@@ -1277,6 +1277,7 @@ struct PtWave {
     float4* L;         // L.rgb, unused
     uint4* rng;        // state lo/hi, inc lo/hi
     float4* hit;       // t, tidx (bits), iidx (bits), sort key (bits)
+    float2* hit_uv;    // barycentric weights of vertex 1 and 2 of the hit; only allocated when a mesh carries uv / colour streams (else NULL)
     uint32_t* active;  // slots alive this bounce
     uint32_t* next;    // slots alive next bounce
     uint32_t* sorted;  // active, reordered by material key
@@ -1327,6 +1328,7 @@ struct PtExtendJob {
         uint32_t key = PT_KEY_MISS;
         if (h.prim != PT_NONE) key = min(h.mat, PT_KEY_BUCKETS - 1u);
         w.hit[s] = make_float4(h.t, __uint_as_float(h.tidx), __uint_as_float(h.iidx), __uint_as_float(key));
+        if (w.hit_uv && h.prim != PT_NONE) w.hit_uv[s] = make_float2(pt_div(h.U, h.ad), pt_div(h.V, h.ad));
     }
 };
 template <bool TWO_LEVEL>
@@ -1384,13 +1386,18 @@ __global__ void k_key_clear(uint32_t* key_hist) {
 struct PtShadeScene {
     PtSceneView sv;
     const PtMaterial* mats; uint32_t num_mats;
+    const PtMeshAttr* mesh_attr;      // per mesh, or NULL when no mesh has uv / colour streams (the default path is then untouched)
+    const PtTexture* textures; const uint32_t* mat_tex;
     PtShadeConsts sc;
 };
 
 // B3 + B4 (+ the compaction half of B6): shade every active path; ballot/popc compaction of survivors and
 // of the emitted shadow rays (one atomic per warp each).
+#ifndef PT_SHADE_MIN_BLOCKS
+#define PT_SHADE_MIN_BLOCKS 6     // 80 registers, no spill: -3 % / -6 % shade time on configs 2 / 4, +-0 on config 3 vs 100 registers; 64 registers (8 blocks) spills and is 20 % slower (profiles/r02_ab_shade_occupancy.log)
+#endif
 template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(128) k_shade(PtShadeScene ss, PtWave w, const uint32_t* list) {
+__global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(PtShadeScene ss, PtWave w, const uint32_t* list) {
     const uint32_t n = w.ctr->n_active;
     const uint32_t rounds = (n + pt_gsize() - 1) / pt_gsize();
     for (uint32_t r = 0; r < rounds; ++r) {
@@ -1423,6 +1430,13 @@ __global__ void __launch_bounds__(128) k_shade(PtShadeScene ss, PtWave w, const 
                 }
                 uint32_t mi = t1.w < ss.num_mats ? t1.w : 0u;
                 PtMaterial mat = ss.mats[mi];
+                if (ss.mesh_attr) {   // base colour x interpolated vertex colour x albedo texel (the reference's fragment shader, Triangle.slang:34-37)
+                    uint32_t mesh = 0;
+                    if (TWO_LEVEL) mesh = pt_ldg4(ss.sv.instances + 7 * (size_t)__float_as_uint(h.z) + 6).z;
+                    const uint32_t prim = pt_ldg4(ss.sv.tris + 3 * (size_t)tidx).w;
+                    const float2 buv = w.hit_uv[s];
+                    pt_material_apply_attributes(&mat, ss.mesh_attr[mesh], ss.textures, ss.mat_tex[mi], prim, buv.x, buv.y);
+                }
                 alive = pt_shade_vertex(&p, ss.sc, h.x, e1, e2, mat, &sh);
                 shadow = sh.valid;
             }

@@ -121,6 +121,66 @@ PT_HD void pt_path_init(PtPath* p, const PtCamera& cam, uint64_t seed, uint32_t 
     p->bounce = 0;
 }
 
+// ---- per-vertex attributes and the albedo texture -------------------------------------------------------
+// The only material inputs the reference's renderer has: `vertex_input {pos, color, texCoord}` (mos9527/Foundation
+// src/Renderer/Renderer.cpp:23-27, the quad at :153-157) and one RGBA8 texture sampled in the fragment shader,
+// `texture.Sample(sampler, uv) * float4(color, 1)` (src/Renderer/Triangle.slang:34-37), through a sampler with the RHI's defaults —
+// linear filter, REPEAT addressing (src/Platform/RHI/Device.hpp:71-99; the image has one mip level, so anisotropy / mip modes are moot).
+// Here the product enters the surface model as the base colour:  base = material.base_color * colour(u, v) * texel(uv(u, v)).
+// Same arithmetic rule as the rest of this file (+ - * / fma, fixed order), so the device and the oracle agree to the bit.
+struct PtTexture { const uint32_t* texels; uint32_t width, height, pad; };   // R8G8B8A8_UNORM (format of Renderer.cpp:205), rows from the top, tightly packed
+struct PtMeshAttr {                                                          // per mesh; NULL stream = attribute absent (colour 1, no uv)
+    const uint8_t* uv; const uint8_t* col; const void* idx;
+    uint32_t uv_stride, col_stride, idx_fmt /* 32, 16, 0 = unindexed */, pad;
+};
+PT_HD float pt_wrap01(float x) {      // x - floor(x) in [0, 1); 0 for NaN / inf / |x| >= 2^23 (no fractional bits left)
+    if (!(pt_abs(x) < 8388608.0f)) return 0.0f;
+    float f = x - pt_floor(x);
+    return f < 1.0f ? f : 0.0f;       // -1e-9 - floor(-1e-9) rounds to 1
+}
+PT_HD pt_v3 pt_texel(const PtTexture& t, uint32_t x, uint32_t y) {
+    uint32_t p = t.texels[(size_t)y * t.width + x];
+    const float k = 0.00392156885936856270f;   // float(1 / 255)
+    return pt_mk((float)(p & 0xffu) * k, (float)((p >> 8) & 0xffu) * k, (float)((p >> 16) & 0xffu) * k);
+}
+// bilinear, REPEAT in both directions, texel centres at half-integers (Vulkan's unnormalised coordinate u * W - 0.5)
+PT_HD pt_v3 pt_texture_sample(const PtTexture& t, float u, float v) {
+    float x = pt_fma(pt_wrap01(u), (float)t.width, -0.5f), y = pt_fma(pt_wrap01(v), (float)t.height, -0.5f);   // in [-0.5, W - 0.5)
+    float fx0 = pt_floor(x), fy0 = pt_floor(y);
+    float fx = x - fx0, fy = y - fy0;
+    int ix = (int)fx0, iy = (int)fy0;                                                                          // -1 .. W - 1
+    uint32_t x0 = ix < 0 ? t.width - 1u : (uint32_t)ix, y0 = iy < 0 ? t.height - 1u : (uint32_t)iy;
+    uint32_t x1 = x0 + 1u < t.width ? x0 + 1u : 0u, y1 = y0 + 1u < t.height ? y0 + 1u : 0u;
+    pt_v3 c00 = pt_texel(t, x0, y0), c10 = pt_texel(t, x1, y0), c01 = pt_texel(t, x0, y1), c11 = pt_texel(t, x1, y1);
+    pt_v3 a = pt_madd(c00, fx, pt_sub(c10, c00)), b = pt_madd(c01, fx, pt_sub(c11, c01));
+    return pt_madd(a, fy, pt_sub(b, a));
+}
+PT_HD uint32_t pt_attr_index(const PtMeshAttr& a, uint32_t prim, uint32_t k) {
+    if (a.idx_fmt == 32u) return ((const uint32_t*)a.idx)[3 * (size_t)prim + k];
+    if (a.idx_fmt == 16u) return ((const uint16_t*)a.idx)[3 * (size_t)prim + k];
+    return 3u * prim + k;
+}
+// base colour of the hit: material x interpolated vertex colour x texel.  bu, bv: barycentric weights of vertex 1 and 2 (the hit record's u, v).
+PT_HD void pt_material_apply_attributes(PtMaterial* m, const PtMeshAttr& a, const PtTexture* textures, uint32_t tex_id, uint32_t prim, float bu, float bv) {
+    if (!a.uv && !a.col) return;
+    uint32_t i0 = pt_attr_index(a, prim, 0), i1 = pt_attr_index(a, prim, 1), i2 = pt_attr_index(a, prim, 2);
+    float w0 = (1.0f - bu) - bv;
+    if (a.col) {
+        const float *c0 = (const float*)(a.col + (size_t)i0 * a.col_stride), *c1 = (const float*)(a.col + (size_t)i1 * a.col_stride),
+                    *c2 = (const float*)(a.col + (size_t)i2 * a.col_stride);
+        m->r *= pt_fma(bv, c2[0], pt_fma(bu, c1[0], w0 * c0[0]));
+        m->g *= pt_fma(bv, c2[1], pt_fma(bu, c1[1], w0 * c0[1]));
+        m->b *= pt_fma(bv, c2[2], pt_fma(bu, c1[2], w0 * c0[2]));
+    }
+    if (a.uv && tex_id != PT_NONE) {
+        const float *t0 = (const float*)(a.uv + (size_t)i0 * a.uv_stride), *t1 = (const float*)(a.uv + (size_t)i1 * a.uv_stride),
+                    *t2 = (const float*)(a.uv + (size_t)i2 * a.uv_stride);
+        float u = pt_fma(bv, t2[0], pt_fma(bu, t1[0], w0 * t0[0])), v = pt_fma(bv, t2[1], pt_fma(bu, t1[1], w0 * t0[1]));
+        pt_v3 c = pt_texture_sample(textures[tex_id], u, v);
+        m->r *= c.x; m->g *= c.y; m->b *= c.z;
+    }
+}
+
 // ---- surface model ----------------------------------------------------------------------------------
 struct PtBsdf {
     pt_v3 kd, f0;

@@ -52,6 +52,9 @@ SYMBOLS = {
     "foundation_pt_materials_set": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "foundation_pt_mesh_create": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]),
     "foundation_pt_instances_set": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "foundation_pt_mesh_attributes_set": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "foundation_pt_texture_create": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.POINTER(C.c_uint32)]),
+    "foundation_pt_material_textures_set": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "foundation_pt_scene_commit": (C.c_int32, [C.c_void_p, C.POINTER(BuildStats)]),
     "foundation_pt_camera_set": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "foundation_pt_partition_set": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
@@ -183,6 +186,25 @@ class PathTracer:
         self._check(self._lib.foundation_pt_mesh_create(self._ctx, _p(pos), stride, nverts, _p(idx), fmt, ntris, _p(mat), C.byref(out)))
         return out.value
 
+    def mesh_attributes_set(self, mesh_id: int, uv=None, colors=None, uv_stride: int = 8, color_stride: int = 12):
+        """Per-vertex uv (float2) / colour (float3) streams; pass strides for interleaved buffers."""
+        uv = None if uv is None else np.ascontiguousarray(uv); colors = None if colors is None else np.ascontiguousarray(colors)
+        if uv is not None and uv.dtype != np.uint8:
+            uv = np.ascontiguousarray(uv, np.float32)
+        if colors is not None and colors.dtype != np.uint8:
+            colors = np.ascontiguousarray(colors, np.float32)
+        self._check(self._lib.foundation_pt_mesh_attributes_set(self._ctx, mesh_id, _p(uv), uv_stride, _p(colors), color_stride))
+
+    def texture_create(self, rgba8, row_pitch: int = 0) -> int:
+        t = np.ascontiguousarray(rgba8, np.uint8); assert t.ndim == 3 and t.shape[2] == 4
+        out = C.c_uint32()
+        self._check(self._lib.foundation_pt_texture_create(self._ctx, _p(t), t.shape[1], t.shape[0], row_pitch, C.byref(out)))
+        return out.value
+
+    def material_textures_set(self, ids):
+        a = np.ascontiguousarray(ids, np.uint32)
+        self._check(self._lib.foundation_pt_material_textures_set(self._ctx, _p(a), a.shape[0]))
+
     def instances_set(self, instances):
         inst = np.ascontiguousarray(instances)
         assert inst.dtype.itemsize == 64
@@ -197,7 +219,13 @@ class PathTracer:
     def load(self, scene: Scene) -> BuildStats:
         self.materials_set(scene.materials)
         for m in scene.meshes:
-            self.mesh_create(m.positions, m.indices, m.material_ids)
+            mid = self.mesh_create(m.positions, m.indices, m.material_ids)
+            if getattr(m, "uv", None) is not None or getattr(m, "colors", None) is not None:
+                self.mesh_attributes_set(mid, m.uv, m.colors)
+        for tex in getattr(scene, "textures", None) or []:
+            self.texture_create(tex)
+        if getattr(scene, "material_textures", None) is not None:
+            self.material_textures_set(scene.material_textures)
         if scene.instances is not None:
             self.instances_set(scene.instances)
         bs = self.scene_commit()

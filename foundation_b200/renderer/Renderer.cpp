@@ -102,6 +102,8 @@ void Renderer::Draw() {
     Check(foundation_pt_resolve_rgba8(m_ctx, m_present_image, (size_t)m_width * m_height * 4), "resolve_rgba8");
 }
 
+void Renderer::ResolveRGBA8(uint8_t* dst, size_t size_bytes) { Check(foundation_pt_resolve_rgba8(m_ctx, dst, size_bytes), "resolve_rgba8"); }
+
 void Renderer::ReadAccum(std::vector<float>* rgba) const {
     rgba->resize((size_t)m_width * m_height * 4);
     Check(foundation_pt_read_accum(m_ctx, rgba->data(), rgba->size() * sizeof(float)), "read_accum");

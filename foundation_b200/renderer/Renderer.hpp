@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/foundation_pt.h"
+#include "Present.hpp"
 
 namespace Foundation {
 namespace Core {
@@ -59,7 +60,7 @@ struct SceneDesc {
     bool Load(const char* path, std::string* error);  // "FPTS" file written by foundation_b200.scenes.save_scene
 };
 
-class Renderer {
+class Renderer : public FrameSource {   // FrameSource: what PresentUploader (Present.hpp, the RHI-side hand-off) pulls the RGBA8 frame through
     Core::Allocator* m_allocator{nullptr};
     DeviceHandle m_device;
     foundation_pt_group* m_group{nullptr};   // one member per device; the frame is gathered into member 0 inside foundation_pt_group_render
@@ -88,6 +89,10 @@ public:
     void SetInstances(const foundation_pt_instance* instances, uint32_t count);
     void Draw();                                                   // one sample batch + resolve to the present image (blocking, like Renderer.cpp:394)
     const uint8_t* PresentImage() const { return m_present_image; }
+    // FrameSource
+    uint32_t FrameWidth() const override { return m_width; }
+    uint32_t FrameHeight() const override { return m_height; }
+    void ResolveRGBA8(uint8_t* dst, size_t size_bytes) override;   // accum / spp -> R8G8B8A8_UNORM straight into the caller's (mapped staging) memory
     uint32_t Width() const { return m_width; }
     uint32_t Height() const { return m_height; }
     uint32_t SamplesDone() const { return m_samples_done; }

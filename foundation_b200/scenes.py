@@ -23,6 +23,8 @@ class Mesh:
     positions: np.ndarray      # (V,3) float32
     indices: np.ndarray        # (T,3) uint32
     material_ids: np.ndarray   # (T,)  uint32
+    uv: Optional[np.ndarray] = None       # (V,2) float32 — the reference's vertex_input.texCoord
+    colors: Optional[np.ndarray] = None   # (V,3) float32 — the reference's vertex_input.color
 
 
 @dataclasses.dataclass
@@ -36,6 +38,8 @@ class Scene:
     width: int = 1920
     height: int = 1080
     background: tuple = (0.0, 0.0, 0.0)
+    textures: Optional[list] = None             # list of (H,W,4) uint8 RGBA images
+    material_textures: Optional[np.ndarray] = None   # (M,) uint32: albedo texture id per material, 0xFFFFFFFF = none
 
     @property
     def num_triangles(self) -> int:
@@ -423,6 +427,31 @@ def save_scene(scene: Scene, path: str) -> None:
             f.write(np.asarray([m.positions.shape[0], m.indices.shape[0]], np.uint32).tobytes())
             f.write(np.ascontiguousarray(m.positions, np.float32).tobytes()); f.write(np.ascontiguousarray(m.indices, np.uint32).tobytes())
             f.write(np.ascontiguousarray(m.material_ids, np.uint32).tobytes())
+
+
+def checker_texture(size: int = 64, cells: int = 8, seed: int = 9) -> np.ndarray:
+    """Procedural RGBA8 stand-in for the JPEG the reference downloads at configure time (src/Renderer/CMakeLists.txt:109-115, not
+    available offline): coloured checkerboard with per-cell noise so that bilinear filtering and the REPEAT seam are both exercised."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cell = np.add.outer(np.arange(size) // (size // cells), np.arange(size) // (size // cells)) % 2
+    base = np.where(cell[..., None] == 0, np.asarray([230, 220, 200]), np.asarray([40, 60, 110]))
+    img = np.clip(base + rng.integers(-25, 26, (size, size, 3)), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.concatenate([img, np.full((size, size, 1), 255, np.uint8)], -1))
+
+
+def reference_quad(width: int = 320, height: int = 180) -> Scene:
+    """The scene the reference actually draws: its 4-vertex quad (positions, colours and texture coordinates of
+    src/Renderer/Renderer.cpp:153-157, indices 0 1 2 2 3 0 of :175), its camera (Renderer.cpp:373-380) and a texture bound to the quad's
+    material, path traced under a constant white environment instead of rasterised: the primary hit's base colour is texel x vertex colour,
+    the reference's fragment shader (src/Renderer/Triangle.slang:34-37)."""
+    pos = np.asarray([(-0.5, -0.5, 0), (0.5, -0.5, 0), (0.5, 0.5, 0), (-0.5, 0.5, 0)], np.float32)
+    col = np.asarray([(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)], np.float32)
+    uv = np.asarray([(1, 0), (0, 0), (0, 1), (1, 1)], np.float32)
+    idx = np.asarray([(0, 1, 2), (2, 3, 0)], np.uint32)
+    mesh = Mesh(pos, idx, np.zeros(2, np.uint32), uv, col)
+    mats = np.asarray([_mat((1.0, 1.0, 1.0), 1.0)], np.float32)
+    view, proj = reference_camera(width / height)
+    return Scene("reference_quad", [mesh], mats, None, view, proj, width, height, (1.0, 1.0, 1.0), [checker_texture()], np.asarray([0], np.uint32))
 
 
 def by_name(name: str, **kw) -> Scene:

@@ -156,6 +156,21 @@ FOUNDATION_PT_API int32_t foundation_pt_materials_set(foundation_pt_context* ctx
 FOUNDATION_PT_API int32_t foundation_pt_mesh_create(foundation_pt_context* ctx, const void* positions, size_t pos_stride_bytes,
                                                     uint32_t num_vertices, const void* indices, uint32_t index_format,
                                                     uint32_t num_triangles, const uint32_t* material_ids, uint32_t* out_mesh_id);
+/* Optional per-vertex attributes of a mesh — the rest of the reference's `vertex_input {pos, color, texCoord}` (Renderer.cpp:23-27; the
+ * quad's values at :153-157): uv = float2, color = float3, each with its own byte stride (pointers into one interleaved, over-aligned
+ * vertex buffer are fine), one entry per vertex of mesh_create.  Either may be NULL.  The hit's base colour becomes
+ * material.base_color * colour(u, v) * texel(uv(u, v)), the path-traced counterpart of the reference's fragment shader
+ * `texture.Sample(sampler, uv) * float4(color, 1)` (src/Renderer/Triangle.slang:34-37). */
+FOUNDATION_PT_API int32_t foundation_pt_mesh_attributes_set(foundation_pt_context* ctx, uint32_t mesh_id, const void* uv, size_t uv_stride_bytes,
+                                                            const void* color, size_t color_stride_bytes);
+/* R8G8B8A8_UNORM image, rows from the top (what the reference uploads at Renderer.cpp:200-270; row_pitch_bytes 0 = tightly packed).  Sampled
+ * bilinearly with REPEAT addressing: the RHI sampler's defaults (src/Platform/RHI/Device.hpp:71-99, created at Renderer.cpp:272-277;
+ * one mip level, so its anisotropy setting has nothing to act on).  Alpha is ignored. */
+#define FOUNDATION_PT_NO_TEXTURE 0xFFFFFFFFu
+FOUNDATION_PT_API int32_t foundation_pt_texture_create(foundation_pt_context* ctx, const void* rgba8, uint32_t width, uint32_t height, size_t row_pitch_bytes,
+                                                       uint32_t* out_texture_id);
+/* One texture id (or FOUNDATION_PT_NO_TEXTURE) per material of materials_set: the albedo texture of that material. */
+FOUNDATION_PT_API int32_t foundation_pt_material_textures_set(foundation_pt_context* ctx, const uint32_t* texture_ids, uint32_t count);
 /* Optional.  Without it every mesh is instanced once with the identity transform.  A singular transform is reported by the
  * following scene_commit (FOUNDATION_PT_ERR_ARGUMENT): the inverse matrices are computed on the device. */
 FOUNDATION_PT_API int32_t foundation_pt_instances_set(foundation_pt_context* ctx, const foundation_pt_instance* instances, uint32_t count);

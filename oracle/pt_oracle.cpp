@@ -259,6 +259,7 @@ struct Mesh {
     std::vector<uint32_t> mat;
     Box3 bounds; float pad = 0;
     std::vector<uint32_t> order;  // sorted position -> input triangle
+    std::vector<float> uv, col;   // optional per-CORNER attributes (6 / 9 floats per triangle, resolved through the indices like `v`)
     std::vector<PtNode8> nodes;
     std::vector<PtTri> tris;      // leaf order
 };
@@ -273,6 +274,8 @@ struct Scene {
     // TLAS
     std::vector<PtNode8> tnodes; std::vector<PtInstance> tinst; std::vector<uint32_t> torder; Box3 wbounds;
     std::vector<PtLight> lights; float light_area = 0; float ray_eps = 0;
+    struct Tex { std::vector<uint32_t> texels; uint32_t w = 0, h = 0; };
+    std::vector<Tex> textures; std::vector<uint32_t> mat_tex;
     std::vector<PtNode8> fnodes; std::vector<PtTri> ftris;  // device-like flat arrays: [TLAS | BLAS 0 | BLAS 1 ..]
     PtCamera cam; bool committed = false;
 };
@@ -522,7 +525,16 @@ void hit_surface(const Scene& s, const Hit& h, pt_v3* e1, pt_v3* e2, PtMaterial*
     if (s.has_insts) { a = pt_xform_vec(s.insts[h.inst].o2w, a); b = pt_xform_vec(s.insts[h.inst].o2w, b); }
     *e1 = a; *e2 = b;
     uint32_t mi = m.mat[h.prim];
-    *mat = s.mats[mi < s.mats.size() ? mi : 0];
+    mi = mi < s.mats.size() ? mi : 0;
+    *mat = s.mats[mi];
+    if (!m.uv.empty() || !m.col.empty()) {   // base colour x vertex colour x albedo texel: the shared arithmetic, fed with per-corner (unindexed) streams
+        PtMeshAttr a; a.uv = m.uv.empty() ? nullptr : (const uint8_t*)m.uv.data(); a.col = m.col.empty() ? nullptr : (const uint8_t*)m.col.data();
+        a.idx = nullptr; a.uv_stride = 8; a.col_stride = 12; a.idx_fmt = 0; a.pad = 0;
+        std::vector<PtTexture> td(s.textures.size() ? s.textures.size() : 1);
+        for (size_t k = 0; k < s.textures.size(); ++k) { td[k].texels = s.textures[k].texels.data(); td[k].width = s.textures[k].w; td[k].height = s.textures[k].h; td[k].pad = 0; }
+        uint32_t tid = mi < s.mat_tex.size() && s.mat_tex[mi] < s.textures.size() ? s.mat_tex[mi] : PT_NONE;
+        pt_material_apply_attributes(mat, a, td.data(), tid, h.prim, pt_div(h.U, h.ad), pt_div(h.V, h.ad));
+    }
 }
 
 bool owns_pixel(uint32_t x, uint32_t y, uint32_t rank, uint32_t count, uint32_t tile) {
@@ -557,6 +569,29 @@ uint32_t orc_mesh_add(void* p, const float* pos, uint32_t nverts, const uint32_t
         m.mat[i] = mat ? mat[i] : 0;
     }
     return (uint32_t)s->meshes.size() - 1;
+}
+// per-vertex uv (float2, tight) / colour (float3, tight), either may be NULL; idx as in orc_mesh_add
+void orc_mesh_attributes_set(void* p, uint32_t mesh, const float* uv, const float* col, const uint32_t* idx) {
+    Mesh& m = ((Scene*)p)->meshes[mesh];
+    m.uv.clear(); m.col.clear();
+    if (uv) m.uv.resize(6 * (size_t)m.ntris);
+    if (col) m.col.resize(9 * (size_t)m.ntris);
+    for (uint32_t i = 0; i < m.ntris; ++i)
+        for (int k = 0; k < 3; ++k) {
+            uint32_t vi = idx ? idx[3 * (size_t)i + k] : 3 * i + k;
+            if (uv) memcpy(&m.uv[6 * (size_t)i + 2 * k], uv + 2 * (size_t)vi, 8);
+            if (col) memcpy(&m.col[9 * (size_t)i + 3 * k], col + 3 * (size_t)vi, 12);
+        }
+}
+uint32_t orc_texture_add(void* p, const uint32_t* rgba8, uint32_t w, uint32_t h) {
+    Scene* s = (Scene*)p; s->textures.emplace_back();
+    s->textures.back().texels.assign(rgba8, rgba8 + (size_t)w * h); s->textures.back().w = w; s->textures.back().h = h;
+    return (uint32_t)s->textures.size() - 1;
+}
+void orc_material_textures_set(void* p, const uint32_t* ids, uint32_t n) { ((Scene*)p)->mat_tex.assign(ids, ids + n); }
+void orc_texture_sample(const uint32_t* rgba8, uint32_t w, uint32_t h, float u, float v, float* rgb) {
+    PtTexture t; t.texels = rgba8; t.width = w; t.height = h; t.pad = 0;
+    pt_v3 c = pt_texture_sample(t, u, v); rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
 }
 void orc_instances_set(void* p, const uint32_t* mesh_ids, const float* xf, uint32_t n) {
     Scene* s = (Scene*)p; s->insts.resize(n); s->has_insts = true;

@@ -61,6 +61,10 @@ def lib() -> C.CDLL:
         L.orc_mesh_add.restype = C.c_uint32
         L.orc_mesh_add.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_instances_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_mesh_attributes_set.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_texture_add.restype = C.c_uint32; L.orc_texture_add.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_material_textures_set.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_texture_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
         L.orc_blas_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.orc_blas_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_tlas_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -115,7 +119,18 @@ class OracleScene:
         for mesh in scene.meshes:
             pos = np.ascontiguousarray(mesh.positions, np.float32); idx = np.ascontiguousarray(mesh.indices, np.uint32)
             mat = np.ascontiguousarray(mesh.material_ids, np.uint32)
-            self._L.orc_mesh_add(self._h, _p(pos), pos.shape[0], _p(idx), idx.shape[0], _p(mat))
+            mid = self._L.orc_mesh_add(self._h, _p(pos), pos.shape[0], _p(idx), idx.shape[0], _p(mat))
+            uv, col = getattr(mesh, "uv", None), getattr(mesh, "colors", None)
+            if uv is not None or col is not None:
+                uv = None if uv is None else np.ascontiguousarray(uv, np.float32); col = None if col is None else np.ascontiguousarray(col, np.float32)
+                self._L.orc_mesh_attributes_set(self._h, mid, _p(uv), _p(col), _p(idx))
+        for tex in getattr(scene, "textures", None) or []:
+            t = np.ascontiguousarray(tex, np.uint8)
+            self._L.orc_texture_add(self._h, _p(t), t.shape[1], t.shape[0])
+        mt = getattr(scene, "material_textures", None)
+        if mt is not None:
+            mt = np.ascontiguousarray(mt, np.uint32)
+            self._L.orc_material_textures_set(self._h, _p(mt), mt.shape[0])
         if scene.instances is not None:
             ids = np.ascontiguousarray(scene.instances["mesh_id"], np.uint32); xf = np.ascontiguousarray(scene.instances["transform"], np.float32)
             self._L.orc_instances_set(self._h, _p(ids), _p(xf), ids.shape[0])
@@ -212,6 +227,12 @@ def pcg_raw(initstate, initseq, n):
 
 def sobol02(sample, k0=0, k1=0):
     x = C.c_float(); y = C.c_float(); lib().orc_sobol02(sample, k0, k1, C.byref(x), C.byref(y)); return x.value, y.value
+
+
+def texture_sample(rgba8, u, v):
+    t = np.ascontiguousarray(rgba8, np.uint8); out = np.zeros(3, np.float32)
+    lib().orc_texture_sample(_p(t), t.shape[1], t.shape[0], u, v, _p(out))
+    return out
 
 
 def hw_threads():

@@ -83,3 +83,12 @@ def test_cpp_renderer_host_links_against_the_c_abi_only():
     for f in ("Renderer.hpp", "Renderer.cpp", "Editor.cpp"):
         txt = open(os.path.join(rdir, f)).read()
         assert "cuda_runtime" not in txt and "torch" not in txt.replace("no torch", "")
+
+
+def test_rhi_present_path_compiles_and_follows_the_reference_upload_protocol():
+    """Present.cpp (abstract-RHI calls only) builds against the stub subset of the reference's RHI headers and,
+    run against a recording mock, performs the staging upload of mos9527/Foundation src/Renderer/Renderer.cpp:219-251 with the resolved bytes."""
+    rdir = os.path.join(ROOT, "foundation_b200", "renderer")
+    subprocess.run(["make", "-C", rdir, "present_selftest"], check=True, capture_output=True)
+    out = subprocess.run([os.path.join(rdir, "present_selftest")], capture_output=True, text=True)
+    assert out.returncode == 0 and "present path OK" in out.stdout, out.stdout + out.stderr

@@ -546,3 +546,44 @@ def test_randomised_meshes_through_both_emulated_builds():
                 else:
                     nn = E.emu_build_agglomerative(_p(box), _p(cent), C.c_uint32(n), C.c_uint32(leaf), _p(lo), _p(hi), _p(nodes), _p(seq), _p(order), C.c_uint32(tile))
                 assert nn == len(on) and nodes[:nn].tobytes() == on.tobytes() and np.array_equal(order, oo), (trial, n, mode, leaf, tile)
+
+
+def test_sobol02_prefixes_equal_the_published_joe_kuo_sequence():
+    """External pin: with zero scramble keys every 2^k-point prefix of pt_sobol02 is, as a SET, the first 2^k points of the 2-D Sobol
+    sequence with Joe & Kuo's direction numbers as shipped in scipy.stats.qmc (scipy enumerates in Gray-code order, which permutes points
+    only inside such prefixes)."""
+    from scipy.stats import qmc
+    ref = qmc.Sobol(d=2, scramble=False).random_base2(10)
+    ours = np.asarray([orc.sobol02(i, 0, 0) for i in range(1024)])
+    for k in range(0, 11):
+        a = {tuple(np.round(p * (1 << 24)).astype(np.int64)) for p in ours[: 1 << k]}
+        b = {tuple(np.round(p * (1 << 24)).astype(np.int64)) for p in ref[: 1 << k]}
+        assert a == b, k
+
+
+def test_direct_light_under_a_square_emitter_matches_the_analytic_form_factor():
+    """External pin of the light-transport scale (pi factors, area <-> solid-angle pdf, MIS weights summing to one): radiance leaving a
+    rough white floor point straight below the centre of a square diffuse emitter.  Irradiance has a closed form — the differential-area to
+    parallel-rectangle configuration factor (Howell catalogue B-4): E = L_e * pi * F, F = 4 F_corner(a/2, a/2, h),
+    F_corner = 1/(2 pi) [ X/sqrt(1+X^2) atan(Y/sqrt(1+X^2)) + Y/sqrt(1+Y^2) atan(X/sqrt(1+Y^2)) ], X = a/h, Y = b/h.
+    The surface model is Lambert under a dielectric coat (F0 = 0.04), not pure Lambert, so the rendered value may sit a few per cent off
+    albedo / pi * E; the test allows 8 % — a lost or doubled pi, a wrong pdf conversion or a broken MIS weight would be off by 2x or more."""
+    a, h, Le, albedo = 1.0, 1.5, 10.0, 0.8
+    X = Y = (a / 2) / h
+    Fc = (X / np.sqrt(1 + X * X) * np.arctan(Y / np.sqrt(1 + X * X)) + Y / np.sqrt(1 + Y * Y) * np.arctan(X / np.sqrt(1 + Y * Y))) / (2 * np.pi)
+    E = Le * np.pi * 4 * Fc
+    want = albedo / np.pi * E
+    b = scenes._Builder()
+    b.add(*scenes._quad((-50, -50, 0), (50, -50, 0), (50, 50, 0), (-50, 50, 0)), 0)
+    b.add(*scenes._quad((-a / 2, a / 2, h), (a / 2, a / 2, h), (a / 2, -a / 2, h), (-a / 2, -a / 2, h)), 1)          # faces -z
+    mats = np.asarray([scenes._mat((albedo,) * 3, 1.0), scenes._mat((0, 0, 0), 1.0, (Le,) * 3)], np.float32)
+    W = 16
+    # a narrow camera just under the emitter's height, off to the side, looking at the floor point below the emitter's centre
+    view = scenes.look_at((0.6, -0.8, 1.2), (0, 0, 0), (0, 0, 1)); proj = scenes.infinite_perspective(np.radians(0.5), 1.0, 0.1)
+    sc = scenes.Scene("form_factor", [b.mesh()], mats, None, view, proj, W, W)
+    o = OracleScene(sc)
+    spp = 256
+    for flags in (0, 2, 4):                                   # MIS, BSDF sampling only, NEE only: three estimators of the same integral
+        img = o.render(W, W, 11, 0, spp, 1, flags=flags)
+        got = img[..., :3].mean() / spp
+        assert abs(got / want - 1) < 0.08, (flags, got, want)
