@@ -1144,7 +1144,10 @@ struct PtDevCounters { unsigned long long nodes, tris, insts; };
 // Resident CTAs per SM the traversal kernels are compiled for.  Flat scenes: 8 x 128 threads x 64 registers = the whole register
 // file (measured: forcing 10 or 12 CTAs spills and is 25-40 % slower).  Two-level kernels carry the world ray as well and need 80
 // registers: 6 CTAs (forcing 64 registers spills and costs 12 %).
-#define PT_TRACE_MIN_BLOCKS(two_level) ((two_level) ? 6 : 8)
+#ifndef PT_TRACE_FLAT_BLOCKS
+#define PT_TRACE_FLAT_BLOCKS 8
+#endif
+#define PT_TRACE_MIN_BLOCKS(two_level) ((two_level) ? 6 : PT_TRACE_FLAT_BLOCKS)
 template <bool ANY, bool TWO_LEVEL, class Counter, class Job>
 __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, unsigned long long n, unsigned long long* work_counter, uint32_t* status,
                                               Counter& cnt, int fetch_thresh) {
@@ -1177,7 +1180,7 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
         while (active) {
             if (pt_trav_step<ANY, TWO_LEVEL>(sc, &st, stack, &best, cnt) == PT_STEP_DONE) {
                 if (st.sp < 0) atomicOr(status, 1u);       // traversal-stack overflow (pt_trav_step left sp = -1)
-                job.store(idx, best);
+                job.store(idx, best, sc, st.world.o, st.world.d);
                 active = false;
                 break;
             }
@@ -1188,18 +1191,18 @@ __device__ __forceinline__ void pt_warp_trace(const PtSceneView& sc, Job& job, u
 
 // B2 / B5 on explicit ray sets: 32-byte ray records read with two 128-bit loads, 16-byte hit records written
 // with one 128-bit store.
-template <bool ANY>
+template <bool ANY, bool TWO_LEVEL>
 struct PtRaySetJob {
     const float4* __restrict__ rays; float4* __restrict__ hits; uint32_t* __restrict__ inst_out; uint8_t* __restrict__ occ;
     __device__ __forceinline__ void load(unsigned long long i, pt_v3* o, pt_v3* d, float* tmin, float* tmax) const {
         float4 a = __ldcs(rays + 2 * i), b = __ldcs(rays + 2 * i + 1);   // streaming: read once, do not displace BVH nodes from L2
         *o = pt_mk(a.x, a.y, a.z); *d = pt_mk(b.x, b.y, b.z); *tmin = a.w; *tmax = b.w;
     }
-    __device__ __forceinline__ void store(unsigned long long i, const PtHitRec& h) const {
+    __device__ __forceinline__ void store(unsigned long long i, const PtHitRec& h, const PtSceneView& sc, pt_v3 wo, pt_v3 wd) const {
         if (ANY) { occ[i] = h.prim != PT_NONE ? 1 : 0; return; }
         float4 o;
         if (h.prim == PT_NONE) { o.x = __uint_as_float(PT_INF_BITS); o.y = 0.0f; o.z = 0.0f; }
-        else { o.x = h.t; o.y = pt_div(h.U, h.ad); o.z = pt_div(h.V, h.ad); }
+        else { uint32_t mat; o.x = h.t; pt_hit_bary<TWO_LEVEL>(sc, h, wo, wd, &o.y, &o.z, &mat); }
         o.w = __uint_as_float(h.prim);
         __stcs(hits + i, o);                                                  // streaming store (evict-first)
         if (inst_out) __stcs(inst_out + i, h.inst);
@@ -1210,7 +1213,7 @@ template <bool ANY, bool TWO_LEVEL, bool COUNT>
 __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS(TWO_LEVEL)) k_trace_rays(PtSceneView sc, const float4* __restrict__ rays, unsigned long long n, float4* __restrict__ hits,
                                                     uint32_t* __restrict__ inst_out, uint8_t* __restrict__ occ, uint32_t* status, PtDevCounters* counters,
                                                     unsigned long long* work_counter, int fetch_thresh) {
-    PtRaySetJob<ANY> job; job.rays = rays; job.hits = hits; job.inst_out = inst_out; job.occ = occ;
+    PtRaySetJob<ANY, TWO_LEVEL> job; job.rays = rays; job.hits = hits; job.inst_out = inst_out; job.occ = occ;
     if (COUNT) {
         PtCount cnt; cnt.nodes = cnt.tris = cnt.insts = 0;
         pt_warp_trace<ANY, TWO_LEVEL>(sc, job, n, work_counter, status, cnt, fetch_thresh);
@@ -1232,7 +1235,11 @@ __global__ void __launch_bounds__(128) k_trace_brute(PtSceneView sc, const PtIns
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < n;
     float4 a = valid ? rays[2 * i] : make_float4(0, 0, 0, 0), b = valid ? rays[2 * i + 1] : make_float4(0, 0, 0, 0);
-    PtHitRec best; best.t = b.w; best.U = best.V = 0; best.ad = 1; best.prim = PT_NONE; best.inst = PT_NONE; best.tidx = best.iidx = 0; best.mat = 0;
+    PtHitRec best;
+    best.t = b.w; best.prim = PT_NONE; best.inst = PT_NONE; best.tidx = best.iidx = 0;
+#if !PT_SLIM_HIT
+    best.U = best.V = 0; best.ad = 1; best.mat = 0;
+#endif
     PtNoCount nc;
     uint32_t ninst = TWO_LEVEL ? num_inst : 1u;
     for (uint32_t ii = 0; ii < ninst; ++ii) {
@@ -1250,13 +1257,18 @@ __global__ void __launch_bounds__(128) k_trace_brute(PtSceneView sc, const PtIns
             for (uint32_t k = threadIdx.x; k < 3 * cntt; k += blockDim.x) tile[k] = pt_load4(sc.tris + 3 * (size_t)(tri_base + t0) + k);
             __syncthreads();
             if (valid)
-                for (uint32_t k = 0; k < cntt; ++k) pt_test_tri_words(tile[3 * k], tile[3 * k + 1], tile[3 * k + 2], k, r, a.w, inst_id, ii, &best, nc);   // shared-memory words
+                for (uint32_t k = 0; k < cntt; ++k) pt_test_tri_words(tile[3 * k], tile[3 * k + 1], tile[3 * k + 2], tri_base + t0 + k, r, a.w, inst_id, ii, &best, nc);   // shared-memory words
         }
     }
     if (!valid) return;
     float4 o;
     if (best.prim == PT_NONE) { o.x = __uint_as_float(PT_INF_BITS); o.y = 0.0f; o.z = 0.0f; }
-    else { o.x = best.t; o.y = pt_div(best.U, best.ad); o.z = pt_div(best.V, best.ad); }
+    else {
+        PtSceneView sv = sc;
+        if (TWO_LEVEL) sv.instances = reinterpret_cast<const PtU4*>(inst_in);      // the exhaustive search walks the CALLER-order instance list: best.iidx indexes it
+        uint32_t mat;
+        o.x = best.t; pt_hit_bary<TWO_LEVEL>(sv, best, pt_mk(a.x, a.y, a.z), pt_mk(b.x, b.y, b.z), &o.y, &o.z, &mat);
+    }
     o.w = __uint_as_float(best.prim);
     hits[i] = o;
     if (inst_out) inst_out[i] = best.inst;
@@ -1317,23 +1329,35 @@ __global__ void __launch_bounds__(256) k_raygen(PtWave w, PtFrame f) {
 // B2: extend — closest hit for every active path (warp-persistent, dynamic fetch over the active list);
 // writes the hit record with the material sort key.
 struct PtExtendJob {
-    PtWave w; const PtU4* tris;
+    PtWave w; const PtU4* tris; bool two_level;
     __device__ __forceinline__ void load(unsigned long long j, pt_v3* o, pt_v3* d, float* tmin, float* tmax) const {
         uint32_t s = w.active[j];
         float4 a = w.ray_o[s], b = w.ray_d[s];
         *o = pt_mk(a.x, a.y, a.z); *d = pt_mk(b.x, b.y, b.z); *tmin = 0.0f; *tmax = __uint_as_float(PT_INF_BITS);
     }
-    __device__ __forceinline__ void store(unsigned long long j, const PtHitRec& h) const {
+    template <bool TWO_LEVEL>
+    __device__ __forceinline__ void store_impl(unsigned long long j, const PtHitRec& h, const PtSceneView& sc, pt_v3 wo, pt_v3 wd) const {
         uint32_t s = w.active[j];
         uint32_t key = PT_KEY_MISS;
-        if (h.prim != PT_NONE) key = min(h.mat, PT_KEY_BUCKETS - 1u);
+        if (h.prim != PT_NONE) {
+            float u, v; uint32_t mat;
+            if (w.hit_uv) { pt_hit_bary<TWO_LEVEL>(sc, h, wo, wd, &u, &v, &mat); w.hit_uv[s] = make_float2(u, v); }   // only scenes with uv / colour streams need them
+#if PT_SLIM_HIT
+            else mat = pt_ldg4(tris + 3 * (size_t)h.tidx + 1).w;                                                  // material id: word 1 .w of the hit triangle, once per ray
+#else
+            else mat = h.mat;
+#endif
+            key = min(mat, PT_KEY_BUCKETS - 1u);
+        }
         w.hit[s] = make_float4(h.t, __uint_as_float(h.tidx), __uint_as_float(h.iidx), __uint_as_float(key));
-        if (w.hit_uv && h.prim != PT_NONE) w.hit_uv[s] = make_float2(pt_div(h.U, h.ad), pt_div(h.V, h.ad));
+    }
+    __device__ __forceinline__ void store(unsigned long long j, const PtHitRec& h, const PtSceneView& sc, pt_v3 wo, pt_v3 wd) const {
+        if (two_level) store_impl<true>(j, h, sc, wo, wd); else store_impl<false>(j, h, sc, wo, wd);
     }
 };
 template <bool TWO_LEVEL>
 __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS(TWO_LEVEL)) k_extend(PtSceneView sc, PtWave w, uint32_t* status, int fetch_thresh) {
-    PtExtendJob job; job.w = w; job.tris = sc.tris;
+    PtExtendJob job; job.w = w; job.tris = sc.tris; job.two_level = TWO_LEVEL;
     PtNoCount nc;
     pt_warp_trace<false, TWO_LEVEL>(sc, job, (unsigned long long)w.ctr->n_active, &w.ctr->work_extend, status, nc, fetch_thresh);
 }
@@ -1479,7 +1503,7 @@ struct PtConnectJob {
         float4 a = w.sh_o[q], b = w.sh_d[q];
         *o = pt_mk(a.x, a.y, a.z); *d = pt_mk(b.x, b.y, b.z); *tmin = 0.0f; *tmax = a.w;
     }
-    __device__ __forceinline__ void store(unsigned long long q, const PtHitRec& h) const {
+    __device__ __forceinline__ void store(unsigned long long q, const PtHitRec& h, const PtSceneView&, pt_v3, pt_v3) const {
         if (h.prim != PT_NONE) return;
         uint32_t s = __float_as_uint(w.sh_d[q].w);
         float4 c = w.sh_c[q], L = w.L[s];

@@ -71,6 +71,9 @@ PT_HD float pt_qfloat(uint32_t w, int i, uint32_t qbias) { return __uint_as_floa
 PT_HD float pt_qfloat(uint32_t w, int i, uint32_t qbias) { return pt_u2f(qbias | (pt_byte(w, i) << 8)); }
 #endif
 
+#ifndef PT_NODE_LOADS_LATE
+#define PT_NODE_LOADS_LATE 0
+#endif
 #ifndef PT_NODE_F32X2
 #define PT_NODE_F32X2 1      // 24 FFMA2 instead of 48 FFMA per node test.  Same-box A/B (profiles/r02_ab_traversal_build.log): +1.9 % spp/s, +2.5 % any-hit,
                              // -1 % on the closest-hit ray sets: the node test is bound by the ALU pipe (PRMT / FMNMX / LOP3) and by load latency, not by the fma pipe
@@ -145,14 +148,21 @@ PT_HD uint32_t pt_node_hits(const PtU4& n0, const PtU4& n1, const PtU4& n2, cons
     return mask;
 }
 
+#ifndef PT_SLIM_HIT
+#define PT_SLIM_HIT 1
+#endif
 struct PtHitRec {
-    float t, U, V, ad;   // undivided barycentrics U, V and |det|
+    float t;
+#if !PT_SLIM_HIT
+    float U, V, ad;   // undivided barycentrics U, V and |det|
+#endif
     uint32_t prim, inst;
-    uint32_t tidx, iidx;  // position of the triangle / instance record in the leaf-ordered device arrays (for shading)
-    uint32_t mat;         // material id of the hit triangle (word 1 .w of the record).  Keeping it live also stops ptxas from recycling
-                          // that register as a scratch right behind the load (a write-after-write stall that serialised the triangle
-                          // and node fetches and cost 8 %)
-};
+    uint32_t tidx, iidx;  // position of the triangle / instance record in the leaf-ordered device arrays (for shading, and for pt_hit_bary)
+#if !PT_SLIM_HIT
+    uint32_t mat;         // material id of the hit triangle (word 1 .w of the record)
+#endif
+};   // PT_SLIM_HIT: the barycentrics and the material id of the FINAL hit are re-derived once per ray from (tidx, iidx) — pt_hit_bary, one extra
+     // triangle fetch per hitting ray — instead of being carried through the traversal loop: four registers less in a loop that sits at the cap
 
 // one ray / triangle test against the current best; a, b, c are the triangle's three 16-byte words
 // `keep` is PtSceneView::zero (0 at run time, opaque to the compiler): OR-ing the two unused .w lanes of the triangle words into
@@ -169,8 +179,11 @@ PT_HD void pt_test_tri_words(const PtU4& a, const PtU4& b, const PtU4& c, uint32
                    pt_mk(pt_u2f(c.x), pt_u2f(c.y), pt_u2f(c.z)), &t, &U, &V, &ad)) {
         uint64_t id = ((uint64_t)inst << 32) | a.w, bid = ((uint64_t)best->inst << 32) | best->prim;
         if (pt_closer(t, id, tmin, best->t, bid, best->prim != PT_NONE)) {
-            best->t = t; best->U = U; best->V = V; best->ad = ad; best->prim = a.w | ((b.w | c.w) & keep); best->inst = inst;
-            best->tidx = tri_index; best->iidx = iidx; best->mat = b.w;
+            best->t = t; best->prim = a.w | ((b.w | c.w) & keep); best->inst = inst;
+            best->tidx = tri_index; best->iidx = iidx;
+#if !PT_SLIM_HIT
+            best->U = U; best->V = V; best->ad = ad; best->mat = b.w;
+#endif
         }
     }
 }
@@ -201,8 +214,11 @@ enum { PT_STEP_RUNNING = 0, PT_STEP_DONE = 1 };
 
 template <bool TWO_LEVEL>
 PT_HD void pt_trav_init(PtTravState* s, pt_v3 o, pt_v3 d, float tmin, float tmax, PtHitRec* best, uint32_t tlas_base = 0) {
-    best->t = tmax; best->U = 0.0f; best->V = 0.0f; best->ad = 1.0f; best->prim = PT_NONE; best->inst = PT_NONE;
-    best->tidx = 0; best->iidx = 0; best->mat = 0;
+    best->t = tmax; best->prim = PT_NONE; best->inst = PT_NONE;
+    best->tidx = 0; best->iidx = 0;
+#if !PT_SLIM_HIT
+    best->U = 0.0f; best->V = 0.0f; best->ad = 1.0f; best->mat = 0;
+#endif
     pt_ray_ctx(&s->world, o, d);
     s->r = s->world;
     s->tmin = tmin;
@@ -256,7 +272,9 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, Stack& stack, PtHi
         }
     }
     const PtU4* np = sc.nodes + 5 * (size_t)(nbase + child);
+#if !PT_NODE_LOADS_LATE
     const PtU4 n0 = pt_load4(np), n1 = pt_load4(np + 1), n2 = pt_load4(np + 2), n3 = pt_load4(np + 3), n4 = pt_load4(np + 4);
+#endif
     if (do_tri) {
         if (leaf_tri) {
             pt_test_tri_words(ta, tb, tc, tri_index, s->r, s->tmin, s->cur_inst, s->cur_iidx, best, cnt, sc.zero);
@@ -279,6 +297,14 @@ PT_HD int pt_trav_step(const PtSceneView& sc, PtTravState* s, Stack& stack, PtHi
             s->tg.x = 0; s->tg.y = 0;
         }
     }
+#if PT_NODE_LOADS_LATE
+    // variant: the node's five words are requested only after the triangle test (20 registers less across the test, but the two round
+    // trips of a lane that does both in one step no longer overlap): measured -1 % at 8 CTAs / SM (profiles/r02_ab_traversal_build.log, run r2d)
+#if defined(__CUDA_ARCH__)
+    asm volatile("" ::: "memory");
+#endif
+    const PtU4 n0 = pt_load4(np), n1 = pt_load4(np + 1), n2 = pt_load4(np + 2), n3 = pt_load4(np + 3), n4 = pt_load4(np + 4);
+#endif
     if (do_node) {   // children are culled against the best hit INCLUDING the triangle tested just above
         cnt.node();
         uint32_t hits = pt_node_hits(n0, n1, n2, n3, n4, s->r, s->tmin, best->t, sc.qbias);
@@ -306,4 +332,29 @@ PT_HD bool pt_traverse(const PtSceneView& sc, pt_v3 o, pt_v3 d, float tmin, floa
     pt_trav_init<TWO_LEVEL>(&s, o, d, tmin, tmax, best, sc.tlas_base);
     while (pt_trav_step<ANY, TWO_LEVEL>(sc, &s, stack, best, cnt) == PT_STEP_RUNNING) {}
     return s.sp >= 0;
+}
+
+// Barycentrics (weights of vertex 1 and 2) and material id of a finished closest hit.  With PT_SLIM_HIT they are re-derived from the hit triangle
+// and — in a two-level scene — the instance the hit lies in: the world ray goes through the same world -> object transform as during the
+// traversal and through the same pt_ray_tri, so the values are bit for bit the ones the loop would have carried.  wo / wd: the world-space ray.
+template <bool TWO_LEVEL>
+PT_HD void pt_hit_bary(const PtSceneView& sc, const PtHitRec& h, pt_v3 wo, pt_v3 wd, float* u, float* v, uint32_t* mat) {
+#if PT_SLIM_HIT
+    pt_v3 o = wo, d = wd;
+    if (TWO_LEVEL) {
+        const PtU4* ip = sc.instances + 7 * (size_t)h.iidx;
+        const PtU4 m0 = pt_load4(ip), m1 = pt_load4(ip + 1), m2 = pt_load4(ip + 2);
+        const float w2o[12] = {pt_u2f(m0.x), pt_u2f(m0.y), pt_u2f(m0.z), pt_u2f(m0.w), pt_u2f(m1.x), pt_u2f(m1.y),
+                               pt_u2f(m1.z), pt_u2f(m1.w), pt_u2f(m2.x), pt_u2f(m2.y), pt_u2f(m2.z), pt_u2f(m2.w)};
+        o = pt_xform_point(w2o, wo); d = pt_xform_vec(w2o, wd);
+    }
+    const PtU4* tp = sc.tris + 3 * (size_t)h.tidx;
+    const PtU4 a = pt_load4(tp), b = pt_load4(tp + 1), c = pt_load4(tp + 2);
+    float t, U = 0.0f, V = 0.0f, ad = 1.0f;
+    pt_ray_tri(o, d, pt_mk(pt_u2f(a.x), pt_u2f(a.y), pt_u2f(a.z)), pt_mk(pt_u2f(b.x), pt_u2f(b.y), pt_u2f(b.z)), pt_mk(pt_u2f(c.x), pt_u2f(c.y), pt_u2f(c.z)), &t, &U, &V, &ad);
+    *u = pt_div(U, ad); *v = pt_div(V, ad); *mat = b.w;
+#else
+    (void)sc; (void)wo; (void)wd;
+    *u = pt_div(h.U, h.ad); *v = pt_div(h.V, h.ad); *mat = h.mat;
+#endif
 }

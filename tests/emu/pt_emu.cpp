@@ -141,7 +141,11 @@ int emu_trace(const void* nodes, const void* tris, const void* instances, int tw
         if (!fine) ok = 0;
         if (any) { occ[i] = h.prim != PT_NONE; continue; }
         if (h.prim == PT_NONE) { hits[i] = EmuHit{INFINITY, 0, 0, PT_NONE}; if (inst_out) inst_out[i] = PT_NONE; }
-        else { hits[i] = EmuHit{h.t, pt_div(h.U, h.ad), pt_div(h.V, h.ad), h.prim}; if (inst_out) inst_out[i] = h.inst; }
+        else {
+            float u, v; uint32_t mat;
+            if (two_level) pt_hit_bary<true>(sc, h, o, d, &u, &v, &mat); else pt_hit_bary<false>(sc, h, o, d, &u, &v, &mat);
+            hits[i] = EmuHit{h.t, u, v, h.prim}; if (inst_out) inst_out[i] = h.inst;
+        }
     }
     if (counters) { counters[0] = c.nodes; counters[1] = c.tris; counters[2] = c.insts; }
     return ok;
