@@ -553,7 +553,8 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
         mark(0);
         for (uint32_t b = 0; b <= max_bounces; ++b) {
             if (sort) PT_LAUNCH(ctx, k_key_clear, 2, 1024, w.key_hist);
-            PT_LAUNCH(ctx, k_extend<TWO>, gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
+            if (w.hit_uv) PT_LAUNCH(ctx, (k_extend<TWO, true>), gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
+            else PT_LAUNCH(ctx, (k_extend<TWO, false>), gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
             mark(1);
             const uint32_t* list = w.active;
             if (sort) {

@@ -1328,6 +1328,7 @@ __global__ void __launch_bounds__(256) k_raygen(PtWave w, PtFrame f) {
 
 // B2: extend — closest hit for every active path (warp-persistent, dynamic fetch over the active list);
 // writes the hit record with the material sort key.
+template <bool ATTR>
 struct PtExtendJob {
     PtWave w; const PtU4* tris; bool two_level;
     __device__ __forceinline__ void load(unsigned long long j, pt_v3* o, pt_v3* d, float* tmin, float* tmax) const {
@@ -1335,6 +1336,7 @@ struct PtExtendJob {
         float4 a = w.ray_o[s], b = w.ray_d[s];
         *o = pt_mk(a.x, a.y, a.z); *d = pt_mk(b.x, b.y, b.z); *tmin = 0.0f; *tmax = __uint_as_float(PT_INF_BITS);
     }
+#if PT_SLIM_HIT
     template <bool TWO_LEVEL>
     __device__ __forceinline__ void store_impl(unsigned long long j, const PtHitRec& h, const PtSceneView& sc, pt_v3 wo, pt_v3 wd) const {
         uint32_t s = w.active[j];
@@ -1342,11 +1344,7 @@ struct PtExtendJob {
         if (h.prim != PT_NONE) {
             float u, v; uint32_t mat;
             if (w.hit_uv) { pt_hit_bary<TWO_LEVEL>(sc, h, wo, wd, &u, &v, &mat); w.hit_uv[s] = make_float2(u, v); }   // only scenes with uv / colour streams need them
-#if PT_SLIM_HIT
             else mat = pt_ldg4(tris + 3 * (size_t)h.tidx + 1).w;                                                  // material id: word 1 .w of the hit triangle, once per ray
-#else
-            else mat = h.mat;
-#endif
             key = min(mat, PT_KEY_BUCKETS - 1u);
         }
         w.hit[s] = make_float4(h.t, __uint_as_float(h.tidx), __uint_as_float(h.iidx), __uint_as_float(key));
@@ -1354,10 +1352,20 @@ struct PtExtendJob {
     __device__ __forceinline__ void store(unsigned long long j, const PtHitRec& h, const PtSceneView& sc, pt_v3 wo, pt_v3 wd) const {
         if (two_level) store_impl<true>(j, h, sc, wo, wd); else store_impl<false>(j, h, sc, wo, wd);
     }
+#else
+    __device__ __forceinline__ void store(unsigned long long j, const PtHitRec& h, const PtSceneView&, pt_v3, pt_v3) const {
+        uint32_t s = w.active[j];
+        uint32_t key = PT_KEY_MISS;
+        if (h.prim != PT_NONE) key = min(h.mat, PT_KEY_BUCKETS - 1u);
+        w.hit[s] = make_float4(h.t, __uint_as_float(h.tidx), __uint_as_float(h.iidx), __uint_as_float(key));
+        if (ATTR && h.prim != PT_NONE) w.hit_uv[s] = make_float2(pt_div(h.U, h.ad), pt_div(h.V, h.ad));   // only scenes with uv / colour streams carry them (separate
+                                                                                                           // instantiation: the two divisions cost the default kernel a spill)
+    }
+#endif
 };
-template <bool TWO_LEVEL>
+template <bool TWO_LEVEL, bool ATTR>
 __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS(TWO_LEVEL)) k_extend(PtSceneView sc, PtWave w, uint32_t* status, int fetch_thresh) {
-    PtExtendJob job; job.w = w; job.tris = sc.tris; job.two_level = TWO_LEVEL;
+    PtExtendJob<ATTR> job; job.w = w; job.tris = sc.tris; job.two_level = TWO_LEVEL;
     PtNoCount nc;
     pt_warp_trace<false, TWO_LEVEL>(sc, job, (unsigned long long)w.ctr->n_active, &w.ctr->work_extend, status, nc, fetch_thresh);
 }

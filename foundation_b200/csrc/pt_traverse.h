@@ -149,7 +149,9 @@ PT_HD uint32_t pt_node_hits(const PtU4& n0, const PtU4& n1, const PtU4& n2, cons
 }
 
 #ifndef PT_SLIM_HIT
-#define PT_SLIM_HIT 1
+#define PT_SLIM_HIT 0      // 1: barycentrics / material id re-derived once per ray instead of carried through the loop (4 registers less).  Measured
+                           // (profiles/r02_ab_traversal_build.log, run r2g): -1.8 % closest-hit, -1.4 % spp/s at 8 CTAs/SM (the extra triangle fetch per hitting ray costs
+                           // more than the registers buy), and 9 CTAs/SM at 56 registers still spills 12-44 bytes: -7 %.  Off.
 #endif
 struct PtHitRec {
     float t;

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-for rep in 1 2; do for lib in ab_libs/shade_mb4.so ab_libs/shade_mb6.so ab_libs/shade_mb8.so ab_libs/shade_mb10.so; do echo -n "$lib: "; FOUNDATION_PT_LIB=$lib timeout 300 python scripts/probe_render.py terrain 32 2>&1 | tail -1; done; done | tee gpurun_out/r2f_ab_shade.log
-for lib in ab_libs/shade_mb4.so ab_libs/shade_mb6.so ab_libs/shade_mb8.so; do for scn in spheres instanced; do echo -n "$lib: "; FOUNDATION_PT_LIB=$lib timeout 300 python scripts/probe_render.py $scn 16 2>&1 | tail -1; done; done | tee -a gpurun_out/r2f_ab_shade.log
+bash scripts/ab2.sh "--hash" ab_libs/v_f1.so ab_libs/slim_fb8.so ab_libs/slim_fb9.so ab_libs/slim_late_fb9.so 2>&1 | tee gpurun_out/r2g_ab.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/r2g_pytest.log
