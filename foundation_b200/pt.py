@@ -52,6 +52,7 @@ SYMBOLS = {
     "foundation_pt_materials_set": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "foundation_pt_mesh_create": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]),
     "foundation_pt_instances_set": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "foundation_pt_mesh_update_positions": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32]),
     "foundation_pt_mesh_attributes_set": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "foundation_pt_texture_create": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.POINTER(C.c_uint32)]),
     "foundation_pt_material_textures_set": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32]),
@@ -185,6 +186,15 @@ class PathTracer:
         out = C.c_uint32()
         self._check(self._lib.foundation_pt_mesh_create(self._ctx, _p(pos), stride, nverts, _p(idx), fmt, ntris, _p(mat), C.byref(out)))
         return out.value
+
+    def mesh_update_positions(self, mesh_id: int, positions, stride: int = 12):
+        """New vertex positions for an existing mesh (same count / stride / indices); its BLAS is rebuilt by the next scene_commit."""
+        pos = np.ascontiguousarray(positions)
+        if stride == 12 and pos.dtype != np.uint8:
+            pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3); nverts = pos.shape[0]
+        else:
+            nverts = (pos.nbytes - 12) // stride + 1
+        self._check(self._lib.foundation_pt_mesh_update_positions(self._ctx, mesh_id, _p(pos), stride, nverts))
 
     def mesh_attributes_set(self, mesh_id: int, uv=None, colors=None, uv_stride: int = 8, color_stride: int = 12):
         """Per-vertex uv (float2) / colour (float3) streams; pass strides for interleaved buffers."""

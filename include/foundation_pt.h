@@ -156,6 +156,11 @@ FOUNDATION_PT_API int32_t foundation_pt_materials_set(foundation_pt_context* ctx
 FOUNDATION_PT_API int32_t foundation_pt_mesh_create(foundation_pt_context* ctx, const void* positions, size_t pos_stride_bytes,
                                                     uint32_t num_vertices, const void* indices, uint32_t index_format,
                                                     uint32_t num_triangles, const uint32_t* material_ids, uint32_t* out_mesh_id);
+/* Deforming meshes (the reference animates its model every Draw, Renderer.cpp:373): new vertex positions for an
+ * existing mesh, same vertex count, stride and index buffer.  The mesh's BLAS is REBUILT by the next scene_commit (all other BLAS are kept): at
+ * ~1.9 G triangles/s a rebuild costs what a refit would and the tree does not degrade.  Restart the accumulation with render(0, ...). */
+FOUNDATION_PT_API int32_t foundation_pt_mesh_update_positions(foundation_pt_context* ctx, uint32_t mesh_id, const void* positions, size_t pos_stride_bytes,
+                                                              uint32_t num_vertices);
 /* Optional per-vertex attributes of a mesh — the rest of the reference's `vertex_input {pos, color, texCoord}` (Renderer.cpp:23-27; the
  * quad's values at :153-157): uv = float2, color = float3, each with its own byte stride (pointers into one interleaved, over-aligned
  * vertex buffer are fine), one entry per vertex of mesh_create.  Either may be NULL.  The hit's base colour becomes

@@ -6,7 +6,11 @@
 // (SURVEY.md §0, §4, §8c).  There is nothing in the reference to check this oracle against, so it restates
 // the north_star specification instead and validates ITSELF: exhaustive O(N) closest hit (no BVH) is the
 // ground truth for hit IDs; the BVH path must agree with it exactly; the shading model is checked by
-// furnace / reciprocity / estimator-agreement tests (tests/test_oracle_*.py).
+// furnace / reciprocity / estimator-agreement tests (tests/test_oracle.py).
+// What pins this oracle from OUTSIDE the shared headers (nothing in the reference can): the PCG32 demo vector; a numpy float64 exhaustive
+// closest hit written from scratch — the ground truth for MISSED hits, with the epsilons written out and the measured non-watertightness of
+// the Moller-Trumbore form (tests/test_watertight.py); the Sobol (0,2) prefixes against scipy's Joe-Kuo sequence; the radiance under a square
+// emitter against the closed-form configuration factor; the texture sampler against a float64 restatement (tests/test_textures.py).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
 // library.  The product (foundation_b200/csrc) never includes, links or calls anything in oracle/.

@@ -443,3 +443,31 @@ def test_stage_timing_flag_reports_where_a_render_spends_its_time(gpu):
     assert st["extend"] > 0 and st["shade"] > 0 and st["connect"] > 0 and st["raygen"] > 0 and st["accumulate"] > 0 and st["material_sort"] == 0.0
     assert 0.7 * sb.last_ms <= sum(sb.stage_ms) <= 1.02 * sb.last_ms, (sb.last_ms, st)
     a.close(); b.close()
+
+
+def test_deforming_mesh_rebuilds_its_blas_and_matches_a_fresh_build(gpu):
+    """SURVEY.md section 8f rank 3, deforming geometry: mesh_update_positions + scene_commit rebuilds the BLAS of that mesh only and gives exactly
+    what a fresh context builds from the deformed vertices (nodes byte for byte, hits, image) — flat scene and instanced scene."""
+    for name in ("terrain", "instanced"):
+        sc = SMALL_SCENES[name]()
+        tr = pt.PathTracer(sc.width, sc.height, seed=6, background=sc.background); tr.load(sc)
+        other_before = [x.tobytes() for x in tr.blas_download(1)] if len(sc.meshes) > 1 else None
+        m = sc.meshes[0]
+        rng = np.random.default_rng(12)
+        pos2 = (m.positions + rng.normal(0, 0.02 * float(np.ptp(m.positions[:, 2]) + 1e-3), m.positions.shape)).astype(np.float32)
+        tr.mesh_update_positions(0, pos2)
+        tr.scene_commit()
+        sc2 = scenes.Scene(sc.name, [scenes.Mesh(pos2, m.indices, m.material_ids)] + sc.meshes[1:], sc.materials, sc.instances, sc.view, sc.proj, sc.width, sc.height, sc.background)
+        orc = OracleScene(sc2)
+        gn, gt, go = tr.blas_download(0); on, ot, oo = orc.blas(0)
+        assert np.array_equal(go, oo) and gn.tobytes() == on.tobytes() and gt.tobytes() == ot.tobytes(), name
+        if other_before is not None:
+            assert [x.tobytes() for x in tr.blas_download(1)] == other_before            # untouched meshes keep their BLAS
+        rays = ray_mix(sc2)
+        gh, gi = tr.trace_closest(rays); oh, oi = orc.trace_closest(rays)
+        assert gh.tobytes() == oh.tobytes() and np.array_equal(gi, oi), name
+        tr.render(0, 2, 3)
+        assert np.array_equal(tr.read_accum(), orc.render(sc.width, sc.height, 6, 0, 2, 3, background=sc.background)), name
+        with pytest.raises(pt.FoundationPtError):
+            tr.mesh_update_positions(0, pos2[:-1])                                        # topology is fixed
+        tr.close()
