@@ -494,9 +494,10 @@ int32_t setup_wave(Ctx* ctx) {
         PT_CK(cudaStreamSynchronize(ctx->stream));
     } else { ctx->num_slots = W * H; ctx->w_slot_pixel.release(); }
     // several samples per wave: more rays in flight per launch and fewer launches per sample (results unchanged: one slot per
-    // (pixel, sample), accumulated in sample order).  Capped at 64 samples / 16 M slots.
+    // (pixel, sample), accumulated in sample order).  Capped at 64 samples / 32 M slots (5.2 GB of wavefront state): measured on one box at 1080p, 64 spp,
+    // 8 bounces (profiles/r02_ab_wave_samples.log): 8 samples per wave 313 / 438 spp/s (configs 3 / 2), 16 -> 321 / 455, 32 -> 326 / 464 (10 GB).
     ctx->wave_samples = 1;
-    if (ctx->num_slots) { uint64_t k = (16ull << 20) / ctx->num_slots; ctx->wave_samples = (uint32_t)(k < 1 ? 1 : (k > 64 ? 64 : k)); }
+    if (ctx->num_slots) { uint64_t k = (32ull << 20) / ctx->num_slots; ctx->wave_samples = (uint32_t)(k < 1 ? 1 : (k > 64 ? 64 : k)); }
     if (const char* e = getenv("FOUNDATION_PT_WAVE_SAMPLES")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->wave_samples = v; }
     size_t S = (size_t)(ctx->num_slots ? ctx->num_slots : 1) * ctx->wave_samples;
     PT_CK(ctx->w_ray_o.alloc(S * 16)); PT_CK(ctx->w_ray_d.alloc(S * 16)); PT_CK(ctx->w_beta.alloc(S * 16)); PT_CK(ctx->w_L.alloc(S * 16));

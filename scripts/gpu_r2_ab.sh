@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-bash scripts/ab2.sh "--hash" ab_libs/v_f1.so ab_libs/slim_fb8.so ab_libs/slim_fb9.so ab_libs/slim_late_fb9.so 2>&1 | tee gpurun_out/r2g_ab.log
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/r2g_pytest.log
+for w in 8 16 32; do echo -n "wave_samples=$w: "; FOUNDATION_PT_WAVE_SAMPLES=$w timeout 300 python scripts/probe_render.py terrain 64 2>&1 | tail -1; done | tee gpurun_out/r2i_wave_samples.log
+for w in 8 16 32; do echo -n "wave_samples=$w: "; FOUNDATION_PT_WAVE_SAMPLES=$w timeout 300 python scripts/probe_render.py spheres 64 2>&1 | tail -1; done | tee -a gpurun_out/r2i_wave_samples.log
