@@ -843,8 +843,8 @@ __global__ void __launch_bounds__(PT_TOP_NODES) k_collapse_top(PtBvh2 b, uint32_
 // ---------------------------------------------------------------------------------------------------
 // A5, all remaining levels in ONE persistent kernel (round 1: per level a select kernel, two scan kernels, an emit kernel and a host
 // round trip for the level's totals).  The grid is one resident wave (cooperative launch); levels are separated by a grid barrier.
-//   phase 1  every wide node of the level is built by EIGHT lanes (one per child / per slot): lane 0 of the group walks the collapse
-//            plan, then each lane loads one child box, the greedy octant assignment runs as 8 rounds of an 8-lane arg-max (the
+//   phase 1  the collapse plan is walked one lane per node (32 nodes per warp), then every wide node is built by EIGHT lanes (one per child /
+//            per slot), four nodes of the warp at a time: each lane loads one child box, the greedy octant assignment runs as 8 rounds of an 8-lane arg-max (the
 //            thread-per-node form spent ~440 warp instructions per node on it: divergent loops over local-memory arrays), each lane
 //            quantises the child of its slot, and the 80-byte node — everything but child_base / tri_base, which need the level's
 //            prefix sums — leaves through shared memory as coalesced words.  Per node it also records the slot refs and the two counts.
@@ -874,8 +874,8 @@ struct PtCollapseArgs {
 };
 #define PT_CL_THREADS 128
 __global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArgs a) {
-    __shared__ uint32_t s_C[PT_CL_THREADS / 8][8];
-    __shared__ uint32_t s_nc[PT_CL_THREADS / 8];
+    __shared__ uint32_t s_C[PT_CL_THREADS][8];
+    __shared__ uint32_t s_nc[PT_CL_THREADS], s_ref[PT_CL_THREADS];
     __shared__ __align__(16) uint32_t s_node[PT_CL_THREADS / 8][20];
     __shared__ uint32_t s_red[4][PT_CL_THREADS / 32];
     const PtBvh2& b = a.b;
@@ -891,22 +891,29 @@ __global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArg
         const uint32_t lo = min(m, blockIdx.x * seg), hi = min(m, lo + seg);
         uint32_t sum_i = 0, sum_p = 0;
         // ---------------- phase 1
-        for (uint32_t w0 = lo; w0 < hi; w0 += PT_CL_THREADS / 8) {      // block-uniform trip count
-            const uint32_t w = w0 + grp;
-            const bool node_ok = w < hi;
-            uint32_t ref = 0, nc = 0;
-            if (node_ok) ref = __ldcg(cur + w);
-            if (node_ok && k == 0) {
-                uint32_t C[8];
-                int n_c;
-                if (pt_b2_count(b, ref) <= a.max_leaf) { C[0] = ref; n_c = 1; } else n_c = pt_plan_children(b, ref, C);
-                for (int i = 0; i < 8; ++i) s_C[grp][i] = i < n_c ? C[i] : PT_NONE;
-                s_nc[grp] = (uint32_t)n_c;
+        for (uint32_t wb = lo; wb < hi; wb += PT_CL_THREADS) {          // block-uniform trip count; a warp owns 32 consecutive nodes of the step
+            {   // (A) the plan walk, ONE LANE PER NODE: as "lane 0 of every 8-lane group" it ran with 4 lanes per warp and was 24 % of all issued
+                // instructions of the kernel (ncu source page); the children lists go to shared memory for the cooperative part
+                const uint32_t wn = wb + tid;
+                uint32_t C[8]; int n_c = 0; uint32_t r0 = 0;
+                if (wn < hi) {
+                    r0 = __ldcg(cur + wn);
+                    if (pt_b2_count(b, r0) <= a.max_leaf) { C[0] = r0; n_c = 1; } else n_c = pt_plan_children(b, r0, C);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s_C[tid][i] = i < n_c ? C[i] : PT_NONE;
+                s_nc[tid] = (uint32_t)n_c; s_ref[tid] = r0;
             }
             __syncwarp();
-            if (node_ok) nc = s_nc[grp];
+          for (uint32_t sub = 0; sub < 8u; ++sub) {                      // (B) 4 nodes of the warp at a time, 8 lanes each
+            const uint32_t nidx = warp * 32u + sub * 4u + (lane >> 3);   // which of the block's 128 nodes my group builds now
+            const uint32_t w0 = wb + warp * 32u + sub * 4u - warp * 4u;  // so that w0 + warp * 4 is the warp's first node of this sub-step (write-out below)
+            const uint32_t w = wb + nidx;
+            const bool node_ok = w < hi;
+            uint32_t ref = 0, nc = 0;
+            if (node_ok) { ref = s_ref[nidx]; nc = s_nc[nidx]; }
             const bool child_ok = node_ok && k < nc;
-            const uint32_t cref = child_ok ? s_C[grp][k] : PT_NONE;
+            const uint32_t cref = child_ok ? s_C[nidx][k] : PT_NONE;
             PtBox nb, cb;
             nb.lox = nb.loy = nb.loz = nb.hix = nb.hiy = nb.hiz = 0.0f; cb = nb;
             uint32_t ccnt = 0, cfirst = 0;
@@ -1000,6 +1007,7 @@ __global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArg
                 for (uint32_t i = lane; i < nn * 20u; i += 32u) dst[i] = srcw[i];
             }
             __syncwarp();
+          }
         }
         // per-block counts of this level
         sum_i = __reduce_add_sync(PT_FULL, sum_i); sum_p = __reduce_add_sync(PT_FULL, sum_p);
