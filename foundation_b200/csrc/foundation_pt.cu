@@ -21,11 +21,10 @@
 #define PT_COLLAPSE_PERSISTENT 1   // 1: all collapse levels beyond the top in one cooperative kernel (k_collapse_levels); 0: round 1's per-level kernels + host round trips
 #endif
 #ifndef PT_ONESWEEP
-#define PT_ONESWEEP 0        // 0 (default): histogram + look-back scan + scatter kernel per pass; 1: one-sweep form (one up-front histogram kernel, one
-                             // kernel per pass with per-digit decoupled look-back).  Measured on the 10 M-pair sort, same box (profiles/r02_ab_traversal_build.log):
-                             // one-sweep 1.20 ms vs 1.13 ms.  ncu: the one-sweep pass takes 154 us against 89 + 29 + 20 us for scatter + histogram +
-                             // scan: 10 M keys are only 7 waves of tiles, every tile of the first wave has to walk back over all tiles resident
-                             // with it (batched 8 loads per round trip; 16 was slower), and the ranking — not the extra key read — is what a pass costs.
+#define PT_ONESWEEP 1        // 1 (default since the ranking moved to shared-memory atomicOr, 3072-key tiles): one up-front histogram kernel + ONE kernel per pass with
+                             // per-digit decoupled look-back; 0: histogram + look-back scan + scatter kernel per pass.  10 M-pair sort, same box
+                             // (profiles/r02_ab_sort_ranking.log): 0.94 ms vs 1.05 ms (and 1.13 ms for round 1's match_any three-kernel form).  With match_any
+                             // ranking and 2304-key tiles the one-sweep form had been the slower one (1.20 vs 1.13 ms, profiles/r02_ab_traversal_build.log).
 #endif
 #ifndef PT_AGGLOMERATIVE
 #define PT_AGGLOMERATIVE 1   // 1: the radix tree is built bottom-up inside the refit (k_refit_agg, k_refit_agg_up); 0: k_karras + k_refit + k_refit_up
@@ -1354,9 +1353,11 @@ int32_t trace_host_pipelined(Ctx* ctx, const foundation_pt_ray* rays, uint64_t c
     }
     ctx->num_rays = count;
     begin_call(ctx);
-    const uint64_t chunk = 1ull << 22;
     cudaEvent_t done_h2d = ctx->ev2, done_k = ctx->ev3;
-    for (uint64_t b = 0; b < count; b += chunk) {
+    // 2^22-ray chunks (128 MB up, 64 MB down) while the upload is the bottleneck; the last 2^23 rays go in 2^20-ray chunks so that the part of the pipeline
+    // nothing overlaps — the last chunk's traversal and download — is a quarter as long
+    for (uint64_t b = 0, chunk; b < count; b += chunk) {
+        chunk = count - b > (1ull << 23) ? (1ull << 22) : (1ull << 20);
         uint64_t n = count - b < chunk ? count - b : chunk;
         PT_CK(cudaMemcpyAsync(ctx->d_rays.as<uint8_t>() + b * 32, rays + b, n * 32, cudaMemcpyHostToDevice, ctx->stream2));
         PT_CK(cudaEventRecord(done_h2d, ctx->stream2));

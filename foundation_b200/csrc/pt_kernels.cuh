@@ -196,6 +196,53 @@ __global__ void __launch_bounds__(PT_SCAN_THREADS) k_scan_lookback(const uint32_
 // A2: stable LSD radix sort of (uint64 key, uint32 value), 8 bits per pass.
 // Per pass: per-tile digit histogram -> exclusive scan over [digit][tile] -> stable scatter with a tile-local sort.
 // ---------------------------------------------------------------------------------------------------
+// Lanes of the warp whose 8-bit digit equals this lane's (only used when PT_RANK_ATOMIC_OR = 0).  PT_MATCH_BALLOT = 1: eight ballots, one per digit
+// bit, intersected in registers (the form CUB's radix ranking uses); 0: one MATCH.ANY.  Measured on the 10 M-pair three-kernel sort, same box
+// (profiles/r02_ab_sort_ranking.log): MATCH.ANY 1.066 ms, ballots 1.056 ms, shared-memory atomicOr (pt_rank_round) 1.043 ms.
+#ifndef PT_MATCH_BALLOT
+#define PT_MATCH_BALLOT 1
+#endif
+__device__ __forceinline__ uint32_t pt_match_digit8(uint32_t d) {
+#if PT_MATCH_BALLOT
+    uint32_t peers = PT_FULL;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t m = __ballot_sync(PT_FULL, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+#else
+    return __match_any_sync(PT_FULL, d);
+#endif
+}
+// One ranking round of a warp: every lane holds a key with digit d; returns the key's rank among the warp's keys of that digit seen so far
+// (cnt_w: the warp's 256 running counts in shared memory).  PT_RANK_ATOMIC_OR = 1: the peer set is built in shared memory — every lane ORs its
+// lane bit into the digit's word of mask_w (all zero between rounds), then reads the word back — instead of by warp votes: OR is order-independent,
+// so the result is as deterministic as a vote (CUB's WARP_MATCH_ATOMIC_OR).
+#ifndef PT_RANK_ATOMIC_OR
+#define PT_RANK_ATOMIC_OR 1
+#endif
+__device__ __forceinline__ uint32_t pt_rank_round(uint32_t d, uint32_t* cnt_w, uint32_t* mask_w, uint32_t lane, uint32_t lt) {
+#if PT_RANK_ATOMIC_OR
+    atomicOr(&mask_w[d], 1u << lane);
+    __syncwarp();
+    const uint32_t peers = mask_w[d];
+#else
+    (void)mask_w;
+    const uint32_t peers = pt_match_digit8(d);
+#endif
+    const uint32_t old = cnt_w[d];
+    __syncwarp();
+    if (lane == (uint32_t)__ffs(peers) - 1u) {
+        cnt_w[d] = old + (uint32_t)__popc(peers);
+#if PT_RANK_ATOMIC_OR
+        mask_w[d] = 0u;
+#endif
+    }
+    __syncwarp();
+    return old + (uint32_t)__popc(peers & lt);       // rank of this key among the warp's keys with the same digit
+}
 #define PT_RS_THREADS 256
 #ifndef PT_RS_ROUNDS
 #define PT_RS_ROUNDS 5      // keys per thread: 1280-key tiles (measured on the 10 M-key sort: 4 -> 1.23 ms, 5 -> 1.13, 6 -> 1.17, 8 -> 1.31)
@@ -207,10 +254,16 @@ __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_hist(const uint64_t* keys,
     h[threadIdx.x] = 0;
     __syncthreads();
     uint32_t base = blockIdx.x * PT_RS_TILE;
-#pragma unroll 4
+    uint64_t k[PT_RS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < PT_RS_ROUNDS; ++r) {       // all loads of the thread in flight before the first shared-memory atomic
+        uint32_t i = base + r * PT_RS_THREADS + threadIdx.x;
+        k[r] = i < n ? __ldg(keys + i) : 0ull;
+    }
+#pragma unroll
     for (int r = 0; r < PT_RS_ROUNDS; ++r) {
         uint32_t i = base + r * PT_RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+        if (i < n) atomicAdd(&h[(uint32_t)(k[r] >> shift) & 255u], 1u);
     }
     __syncthreads();
     tile_hist[threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
@@ -228,6 +281,11 @@ __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_scatter(const uint64_t* __
                                                               uint32_t* __restrict__ vout, uint32_t n, int shift, const uint32_t* __restrict__ tile_off,
                                                               uint32_t num_tiles) {
     __shared__ uint32_t wh[PT_RS_THREADS / 32][256];
+#if PT_RANK_ATOMIC_OR
+    __shared__ uint32_t wm[PT_RS_THREADS / 32][256];
+#else
+    uint32_t (*wm)[256] = wh;
+#endif
     __shared__ uint32_t dstart[256], goff[256];
     __shared__ uint64_t sbuf[PT_RS_TILE];
     uint32_t* svals = reinterpret_cast<uint32_t*>(sbuf);
@@ -236,7 +294,7 @@ __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_scatter(const uint64_t* __
     const uint32_t n_valid = min((uint32_t)PT_RS_TILE, n - base);
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int w = 0; w < PT_RS_THREADS / 32; ++w) wh[w][tid] = 0;
+    for (int w = 0; w < PT_RS_THREADS / 32; ++w) { wh[w][tid] = 0; if (PT_RANK_ATOMIC_OR) wm[w][tid] = 0; }
     uint64_t key[PT_RS_KEYS];
     uint32_t lp[PT_RS_KEYS];
 #pragma unroll
@@ -248,12 +306,7 @@ __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_scatter(const uint64_t* __
 #pragma unroll
     for (int i = 0; i < PT_RS_KEYS; ++i) {
         uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
-        uint32_t peers = __match_any_sync(PT_FULL, d);
-        uint32_t old = wh[warp][d];
-        __syncwarp();
-        if (lane == (uint32_t)__ffs(peers) - 1u) wh[warp][d] = old + (uint32_t)__popc(peers);
-        __syncwarp();
-        lp[i] = old + (uint32_t)__popc(peers & lt);       // rank of this key among the warp's keys with the same digit
+        lp[i] = pt_rank_round(d, wh[warp], wm[warp], lane, lt);
     }
     __syncthreads();
     {   // thread `tid` owns digit `tid`: exclusive prefix over the warps, then over the digits
@@ -305,10 +358,16 @@ __global__ void __launch_bounds__(PT_RS_THREADS) k_rs_scatter(const uint64_t* __
 // separate histogram kernel + scan kernel per pass (round 1: 3 kernels and 2 extra key reads per pass, 1.13 ms for 10 M pairs).
 // ---------------------------------------------------------------------------------------------------
 #ifndef PT_OS_KPT
-#define PT_OS_KPT 9            // keys per thread: 2304-key tiles
+#define PT_OS_KPT 10           // keys per thread: 2560-key tiles at 64 registers / 4 CTAs per SM (12 keys at 80 registers / 3 CTAs is level: 0.775 vs 0.778 ms for 10 M pairs)
 #endif
 #ifndef PT_OS_LB
 #define PT_OS_LB 8             // predecessors inspected per look-back round trip
+#endif
+#ifndef PT_OS_EARLY_VALS
+#define PT_OS_EARLY_VALS 1
+#endif
+#ifndef PT_OS_MIN_BLOCKS
+#define PT_OS_MIN_BLOCKS 4
 #endif
 #define PT_OS_THREADS 256
 #define PT_OS_TILE (PT_OS_THREADS * PT_OS_KPT)
@@ -350,10 +409,15 @@ __global__ void __launch_bounds__(256) k_rs_hist_scan(uint32_t* hist) {
 // k_rs_scatter (match_any against per-warp counters), then thread d publishes the tile's count of digit d — flag AGG — walks back over the
 // predecessors' words of digit d until it meets an inclusive prefix, publishes its own inclusive prefix — flag INC — and so knows where
 // the tile's run of digit d starts in the output.  status: tiles x 256 words, zero at launch; *ticket zero at launch.
-__global__ void __launch_bounds__(PT_OS_THREADS) k_rs_onesweep(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
+__global__ void __launch_bounds__(PT_OS_THREADS, PT_OS_MIN_BLOCKS) k_rs_onesweep(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
                                                                uint32_t* __restrict__ vout, uint32_t n, int shift, const uint32_t* __restrict__ digit_base,
                                                                uint32_t* status, uint32_t* ticket) {
     __shared__ uint32_t wh[PT_OS_THREADS / 32][256];
+#if PT_RANK_ATOMIC_OR
+    __shared__ uint32_t wm[PT_OS_THREADS / 32][256];
+#else
+    uint32_t (*wm)[256] = wh;
+#endif
     __shared__ uint32_t dstart[256], goff[256];
     __shared__ uint64_t sbuf[PT_OS_TILE];
     __shared__ uint32_t s_tile;
@@ -361,7 +425,7 @@ __global__ void __launch_bounds__(PT_OS_THREADS) k_rs_onesweep(const uint64_t* _
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
-    for (int w = 0; w < PT_OS_THREADS / 32; ++w) wh[w][tid] = 0;
+    for (int w = 0; w < PT_OS_THREADS / 32; ++w) { wh[w][tid] = 0; if (PT_RANK_ATOMIC_OR) wm[w][tid] = 0; }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t base = tile * PT_OS_TILE;
@@ -374,15 +438,24 @@ __global__ void __launch_bounds__(PT_OS_THREADS) k_rs_onesweep(const uint64_t* _
         const uint32_t j = warp * (32 * PT_OS_KPT) + i * 32 + lane;
         key[i] = j < n_valid ? __ldcs(kin + base + j) : ~0ull;     // padding sorts to the very end of the tile and is never written
     }
+#if PT_OS_EARLY_VALS == 2
+#pragma unroll                    // variant: only pull the tile's values into L2 now (no registers held)
+    for (int i = 0; i < PT_OS_KPT; ++i) {
+        const uint32_t j = warp * (32 * PT_OS_KPT) + i * 32 + lane;
+        if (j < n_valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(vin + base + j));
+    }
+#elif PT_OS_EARLY_VALS
+    uint32_t val[PT_OS_KPT];      // the values are requested with the keys: loaded after the keys had left (as the three-kernel scatter does) every one of the
+#pragma unroll                    // twelve shared-memory stores below waited for its own DRAM round trip (ncu: 47 % of the stall samples long-scoreboard, all on them)
+    for (int i = 0; i < PT_OS_KPT; ++i) {
+        const uint32_t j = warp * (32 * PT_OS_KPT) + i * 32 + lane;
+        val[i] = j < n_valid ? __ldcs(vin + base + j) : 0u;
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < PT_OS_KPT; ++i) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
-        const uint32_t peers = __match_any_sync(PT_FULL, d);
-        const uint32_t old = wh[warp][d];
-        __syncwarp();
-        if (lane == (uint32_t)__ffs(peers) - 1u) wh[warp][d] = old + (uint32_t)__popc(peers);
-        __syncwarp();
-        lp[i] = old + (uint32_t)__popc(peers & lt);
+        lp[i] = pt_rank_round(d, wh[warp], wm[warp], lane, lt);
     }
     __syncthreads();
     {   // thread `tid` owns digit `tid`
@@ -444,7 +517,11 @@ __global__ void __launch_bounds__(PT_OS_THREADS) k_rs_onesweep(const uint64_t* _
 #pragma unroll
     for (int i = 0; i < PT_OS_KPT; ++i) {
         const uint32_t j = warp * (32 * PT_OS_KPT) + i * 32 + lane;
+#if PT_OS_EARLY_VALS == 1
+        if (j < n_valid) svals[lp[i]] = val[i];
+#else
         if (j < n_valid) svals[lp[i]] = __ldcs(vin + base + j);
+#endif
     }
     __syncthreads();
 #pragma unroll

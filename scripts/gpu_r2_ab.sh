@@ -1,4 +1,7 @@
+#!/bin/bash
+# same-box A/B of the traversal variants under ab_libs/ (scripts/mkvariant.sh): two interleaved passes of scripts/probe2.py
+# usage: scripts/gpu_r2_ab.sh <log name> <variant> [<variant> ...]
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/r2k_pytest.log
-timeout 900 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -k "triangle_counts or hits_match" 2>&1 | tail -3 | tee -a gpurun_out/r2k_pytest.log
-for rep in 1 2; do for lib in ab_libs/head.so ab_libs/walk32.so; do echo -n "$lib: "; FOUNDATION_PT_LIB=$lib timeout 300 python scripts/probe2.py --hash --spp 0 --log2-rays 20 2>&1 | tail -1; done; done | tee gpurun_out/r2k_ab.log
+log=gpurun_out/$1; shift
+: > $log
+for rep in 1 2; do for v in "$@"; do echo -n "$v: "; FOUNDATION_PT_LIB=ab_libs/$v.so timeout 400 python scripts/probe2.py ${PROBE_ARGS:---builds 1 --spp 8 --log2-rays 24} 2>&1 | tail -1; done; done | tee -a $log
