@@ -949,6 +949,12 @@ struct PtCollapseArgs {
     uint32_t* barrier;      // zero at launch
     uint32_t node_cap;      // capacity of `nodes`
 };
+#ifndef PT_COLLAPSE_TIMING
+#define PT_COLLAPSE_TIMING 0     // debug: block 0 prints the wall time of every level's phases (globaltimer)
+#endif
+#ifndef PT_COLLAPSE_REDUX
+#define PT_COLLAPSE_REDUX 1
+#endif
 #define PT_CL_THREADS 128
 __global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArgs a) {
     __shared__ uint32_t s_C[PT_CL_THREADS][8];
@@ -962,8 +968,15 @@ __global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArg
     uint32_t* cur = a.state[3] ? a.refs_b : a.refs_a;
     uint32_t* nxt = a.state[3] ? a.refs_a : a.refs_b;
     uint32_t epoch = 0, error = 0;
+#if PT_COLLAPSE_TIMING
+    unsigned long long t_lvl[16][4]; uint32_t m_lvl[16]; int n_lvl = 0;
+    auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+#endif
     while (m > 0) {
         if (m > a.cap || (uint64_t)level_start + m > a.node_cap) { error = 1; break; }      // grid-uniform
+#if PT_COLLAPSE_TIMING
+        if (n_lvl < 16) { t_lvl[n_lvl][0] = now(); m_lvl[n_lvl] = m; }
+#endif
         const uint32_t seg = (m + gridDim.x - 1) / gridDim.x;
         const uint32_t lo = min(m, blockIdx.x * seg), hi = min(m, lo + seg);
         uint32_t sum_i = 0, sum_p = 0;
@@ -1009,8 +1022,43 @@ __global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArg
 #pragma unroll
             for (int sl = 0; sl < 8; ++sl) c[sl] = (((sl & 4) ? dx : -dx) + ((sl & 2) ? dy : -dy)) + ((sl & 1) ? dz : -dz);
             // greedy assignment: nc rounds; in each the best (child, free slot) pair of the group wins, ties to the smallest (child, slot)
-            uint32_t slot_used = 0; bool done = !child_ok; int kslot = -1;       // kslot: child index that landed in slot `k` (this lane as a SLOT)
+            int kslot = -1;                                                      // kslot: child index that landed in slot `k` (this lane as a SLOT)
             const uint32_t rounds = __reduce_max_sync(PT_FULL, nc);
+#if PT_COLLAPSE_REDUX
+            // Same greedy rule, a third of the instructions (this loop was 49 % of everything the kernel issued, ncu source page): a lane keeps the
+            // costs of its still-free slots (taken ones become -inf), its proposal is their maximum (FMNMX3 tree; ties -> smallest slot), and the
+            // group's winner comes from two integer butterflies over the 8 lanes: the maximum of the order-preserving integer image of the proposals,
+            // then the smallest (child, slot) key among the lanes that hold it.  -0 is folded into +0 first (x + 0.0f), so integer equality is float
+            // equality.  (redux.sync with one member mask per 8-lane group is NOT the tool: with four different masks in a warp the compiler emits a
+            // loop over the distinct masks, BRA.DIV + CREDUX per group, and nothing is gained — measured.)
+            const float ninf = __uint_as_float(0xff800000u);
+            bool done = !child_ok;
+            float cm[8];
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) cm[sl] = c[sl];
+            for (uint32_t it = 0; it < rounds; ++it) {
+                const float m = fmaxf(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])), fmaxf(fmaxf(cm[4], cm[5]), fmaxf(cm[6], cm[7])));
+                uint32_t bs = 7u;
+#pragma unroll
+                for (int sl = 6; sl >= 0; --sl) bs = cm[sl] == m ? (uint32_t)sl : bs;            // smallest free slot that attains the maximum
+                const uint32_t mb = __float_as_uint(m + 0.0f);
+                const uint32_t u = done ? 0u : ((mb & 0x80000000u) ? ~mb : (mb | 0x80000000u));   // 0: no proposal (every finite float maps above it)
+                uint32_t umax = u;
+#pragma unroll
+                for (int o = 4; o >= 1; o >>= 1) umax = max(umax, __shfl_xor_sync(PT_FULL, umax, o));
+                uint32_t win = (!done && u == umax) ? (k << 3 | bs) : 0xffu;                // both butterflies run warp-wide: a group without proposals
+#pragma unroll                                                                               // (umax = 0) must not leave the shuffles to the others
+                for (int o = 4; o >= 1; o >>= 1) win = min(win, __shfl_xor_sync(PT_FULL, win, o));
+                if (win != 0xffu) {                                                         // group-uniform
+                    const uint32_t wk = win >> 3, ws = win & 7u;
+                    if (wk == k) done = true;
+                    if (ws == k) kslot = (int)wk;
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl) cm[sl] = ws == (uint32_t)sl ? ninf : cm[sl];
+                }
+            }
+#else
+            uint32_t slot_used = 0; bool done = !child_ok;
             for (uint32_t it = 0; it < rounds; ++it) {
                 int bs = -1; float bv = 0.0f;
 #pragma unroll
@@ -1031,6 +1079,7 @@ __global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArg
                     if (ws == k) kslot = (int)wk;
                 }
             }
+#endif
             // the child of my slot: fetch its data from the lane that owns it
             const int src = (int)gl + (kslot >= 0 ? kslot : 0);
             const uint32_t sref = __shfl_sync(PT_FULL, cref, src), scnt = __shfl_sync(PT_FULL, ccnt, src), sfirst = __shfl_sync(PT_FULL, cfirst, src);
@@ -1095,7 +1144,13 @@ __global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArg
             for (int i = 0; i < PT_CL_THREADS / 32; ++i) { si += s_red[0][i]; sp += s_red[1][i]; }
             a.block_sums[2 * blockIdx.x] = si; a.block_sums[2 * blockIdx.x + 1] = sp;
         }
+#if PT_COLLAPSE_TIMING
+        if (n_lvl < 16) t_lvl[n_lvl][1] = now();
+#endif
         pt_grid_barrier(a.barrier, epoch);
+#if PT_COLLAPSE_TIMING
+        if (n_lvl < 16) t_lvl[n_lvl][2] = now();
+#endif
         // ---------------- offsets of this block's segment + the level's totals
         uint32_t pre_i = 0, pre_p = 0, tot_i = 0, tot_p = 0;
         for (uint32_t bb = tid; bb < gridDim.x; bb += PT_CL_THREADS) {
@@ -1137,10 +1192,24 @@ __global__ void __launch_bounds__(PT_CL_THREADS) k_collapse_levels(PtCollapseArg
                 }
             }
         }
+#if PT_COLLAPSE_TIMING
+        if (n_lvl < 16) t_lvl[n_lvl][3] = now();
+#endif
         pt_grid_barrier(a.barrier, epoch);
+#if PT_COLLAPSE_TIMING
+        ++n_lvl;
+#endif
         level_start = next_start; prim_total += tot_p; m = tot_i;
         uint32_t* t = cur; cur = nxt; nxt = t;
     }
+#if PT_COLLAPSE_TIMING
+    if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && tid == 0 && n_lvl > 6) {
+        const unsigned long long t_end = now();
+        for (int i = 0; i < n_lvl && i < 16; ++i)
+            printf("blk %u level %d m %u: phase1 %llu ns, barrier wait %llu ns, phase2 %llu ns, to next level %llu ns\n", blockIdx.x, i, m_lvl[i], t_lvl[i][1] - t_lvl[i][0],
+                   t_lvl[i][2] - t_lvl[i][1], t_lvl[i][3] - t_lvl[i][2], (i + 1 < n_lvl ? t_lvl[i + 1][0] : t_end) - t_lvl[i][3]);
+    }
+#endif
     if (blockIdx.x == 0 && tid == 0) { a.state[0] = m; a.state[1] = level_start; a.state[2] = prim_total; a.state[3] = error; }
 }
 
