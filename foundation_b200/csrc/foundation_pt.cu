@@ -125,6 +125,7 @@ struct foundation_pt_context {
     foundation_pt_config cfg{};
     foundation_pt_allocator host_alloc{};
     int device = 0, num_sms = 0, trace_blocks_per_sm = 0 /* 0 = kernel's own: 8 flat, 6 two-level */, fetch_thresh = 24;
+    int e2e_chunk_log2 = 22, e2e_tail_log2 = 20;   // host-buffer trace calls: rays per pipeline chunk, and per chunk over the last 2^(e2e_chunk_log2 + 1) rays
     int collapse_blocks = 0; // grid of the persistent collapse kernel: one resident wave on this device
     int refit_blocks = 0;   // occupancy of the tiled refit kernel on this context's device (queried at the first build)
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // compute, H2D, D2H
@@ -321,14 +322,16 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
     {   // top of the tree: all levels of at most PT_TOP_NODES wide nodes in one single-block launch
         PT_LAUNCH(ctx, k_collapse_top, 1, PT_TOP_NODES, b, refs_a.as<uint32_t>(), refs_b.as<uint32_t>(), max_leaf, d_bp, nodes_tmp.as<PtNode8>(), out->leaf_seq.as<uint32_t>(),
                   totals.as<uint32_t>());
+#if !PT_COLLAPSE_PERSISTENT
         uint32_t st[4];
         PT_CK(cudaMemcpyAsync(st, totals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
         PT_CK(cudaStreamSynchronize(ctx->stream));
         m = st[0]; level_start = st[1]; prim_total = st[2];
         if (st[3]) std::swap(refs_a, refs_b);
+#endif
     }
 #if PT_COLLAPSE_PERSISTENT
-    if (m > 0) {
+    {
         // every remaining level in one cooperative launch: the grid is one resident wave, levels are separated by a grid barrier and the
         // level totals never leave the device
         if (!ctx->collapse_blocks) {
@@ -347,9 +350,8 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
         ca.b = b; ca.refs_a = refs_a.as<uint32_t>(); ca.refs_b = refs_b.as<uint32_t>(); ca.max_leaf = max_leaf; ca.bp = d_bp; ca.nodes = nodes_tmp.as<PtNode8>();
         ca.leaf_seq = out->leaf_seq.as<uint32_t>(); ca.state = totals.as<uint32_t>(); ca.slots = slots.as<uint32_t>(); ca.n_int = n_int.as<uint32_t>();
         ca.n_prim = n_prim.as<uint32_t>(); ca.cap = cap_level; ca.block_sums = block_sums.as<uint32_t>(); ca.barrier = barrier.as<uint32_t>(); ca.node_cap = n;
-        // k_collapse_top left {m, level_start, prim_total, parity} in `totals`; the host swapped refs_a / refs_b to make parity 0
-        uint32_t st0[4] = {m, level_start, prim_total, 0u};
-        PT_CK(cudaMemcpyAsync(totals.p, st0, 16, cudaMemcpyHostToDevice, ctx->stream));
+        // k_collapse_top left {m, level_start, prim_total, parity} in `totals`: the kernel takes them from there (no host round trip; with m = 0 —
+        // a tree that fits the top kernel — it returns at once)
         void* kargs[] = {&ca};
         PT_CK(cudaLaunchCooperativeKernel((const void*)k_collapse_levels, dim3((unsigned)ctx->collapse_blocks), dim3(PT_CL_THREADS), kargs, 0, ctx->stream));
         ctx->call_launches++; ctx->total_launches++;
@@ -387,7 +389,7 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
     out->num_nodes = level_start;
     PT_CK(out->nodes.alloc((size_t)level_start * sizeof(PtNode8)));
     PT_CK(cudaMemcpyAsync(out->nodes.p, nodes_tmp.p, (size_t)level_start * sizeof(PtNode8), cudaMemcpyDeviceToDevice, ctx->stream));
-    PT_CK(cudaStreamSynchronize(ctx->stream));
+    // no synchronisation here: the scratch buffers are released in stream order, and ev3 lies before the collapse's read-back above
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); out->sort_ms = ms;
     out->order = std::move(vals);
     return 0;
@@ -779,6 +781,8 @@ int32_t foundation_pt_create(const foundation_pt_config* config, const foundatio
         cudaGetLastError();
     }
     if (const char* e = getenv("FOUNDATION_PT_FETCH_THRESH")) { int v = atoi(e); if (v >= 0 && v <= 32) ctx->fetch_thresh = v; }
+    if (const char* e = getenv("FOUNDATION_PT_E2E_CHUNK_LOG2")) { int v = atoi(e); if (v >= 12 && v <= 30) ctx->e2e_chunk_log2 = v; }
+    if (const char* e = getenv("FOUNDATION_PT_E2E_TAIL_LOG2")) { int v = atoi(e); if (v >= 12 && v <= 30) ctx->e2e_tail_log2 = v; }
     if (const char* e = getenv("FOUNDATION_PT_TRACE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->trace_blocks_per_sm = v; }
     ctx->mats.push_back(PtMaterial{0.8f, 0.8f, 0.8f, 0.5f, 0, 0, 0, 0});
     *out_ctx = ctx;
@@ -1356,8 +1360,9 @@ int32_t trace_host_pipelined(Ctx* ctx, const foundation_pt_ray* rays, uint64_t c
     cudaEvent_t done_h2d = ctx->ev2, done_k = ctx->ev3;
     // 2^22-ray chunks (128 MB up, 64 MB down) while the upload is the bottleneck; the last 2^23 rays go in 2^20-ray chunks so that the part of the pipeline
     // nothing overlaps — the last chunk's traversal and download — is a quarter as long
+    const uint64_t big = 1ull << ctx->e2e_chunk_log2, small = 1ull << (ctx->e2e_tail_log2 < ctx->e2e_chunk_log2 ? ctx->e2e_tail_log2 : ctx->e2e_chunk_log2);
     for (uint64_t b = 0, chunk; b < count; b += chunk) {
-        chunk = count - b > (1ull << 23) ? (1ull << 22) : (1ull << 20);
+        chunk = count - b > 2 * big ? big : small;
         uint64_t n = count - b < chunk ? count - b : chunk;
         PT_CK(cudaMemcpyAsync(ctx->d_rays.as<uint8_t>() + b * 32, rays + b, n * 32, cudaMemcpyHostToDevice, ctx->stream2));
         PT_CK(cudaEventRecord(done_h2d, ctx->stream2));
