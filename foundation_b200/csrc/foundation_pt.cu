@@ -129,6 +129,11 @@ struct foundation_pt_context {
     int collapse_blocks = 0; // grid of the persistent collapse kernel: one resident wave on this device
     int refit_blocks = 0;   // occupancy of the tiled refit kernel on this context's device (queried at the first build)
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // compute, H2D, D2H
+    // two waves of a render in flight at once: wave i runs on stream (i even) / stream_b (i odd) with its own copy of the wavefront state, so the tail of every
+    // traversal kernel — a persistent grid whose last warps finish long rays alone — and the latency-bound late bounces overlap the other wave's kernels
+    cudaStream_t stream_b = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_acc[2] = {nullptr, nullptr};
+    int wave_sets = 1;             // copies of the wavefront state (1 or 2)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     mutable std::string err = "no error";
 
@@ -199,6 +204,12 @@ typedef foundation_pt_context Ctx;
 #define PT_LAUNCH(ctx, kernel, grid, block, ...)                        \
     do {                                                                \
         kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);     \
+        (ctx)->call_launches++; (ctx)->total_launches++;                \
+    } while (0)
+
+#define PT_LAUNCH_ON(ctx, st, kernel, grid, block, ...)                 \
+    do {                                                                \
+        kernel<<<(grid), (block), 0, (st)>>>(__VA_ARGS__);              \
         (ctx)->call_launches++; (ctx)->total_launches++;                \
     } while (0)
 
@@ -500,13 +511,24 @@ int32_t setup_wave(Ctx* ctx) {
     ctx->wave_samples = 1;
     if (ctx->num_slots) { uint64_t k = (32ull << 20) / ctx->num_slots; ctx->wave_samples = (uint32_t)(k < 1 ? 1 : (k > 64 ? 64 : k)); }
     if (const char* e = getenv("FOUNDATION_PT_WAVE_SAMPLES")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->wave_samples = v; }
-    size_t S = (size_t)(ctx->num_slots ? ctx->num_slots : 1) * ctx->wave_samples;
+    // FOUNDATION_PT_DUAL_WAVE=0 keeps one copy of the wavefront state (half the memory: 5.2 instead of 10.4 GB at 1080p) and one wave in flight;
+    // per-stage timing needs the stages of a render in one stream
+    ctx->wave_sets = 2;
+    if (const char* e = getenv("FOUNDATION_PT_DUAL_WAVE")) { if (atoi(e) == 0) ctx->wave_sets = 1; }
+    if (ctx->cfg.flags & FOUNDATION_PT_FLAG_STAGE_TIMING) ctx->wave_sets = 1;
+    if (ctx->wave_sets == 2 && !ctx->stream_b) {
+        if (cudaStreamCreateWithFlags(&ctx->stream_b, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_acc[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_acc[1], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ctx->wave_sets = 1; }
+    }
+    const size_t S1 = (size_t)(ctx->num_slots ? ctx->num_slots : 1) * ctx->wave_samples;
+    const size_t S = S1 * (size_t)ctx->wave_sets;
     PT_CK(ctx->w_ray_o.alloc(S * 16)); PT_CK(ctx->w_ray_d.alloc(S * 16)); PT_CK(ctx->w_beta.alloc(S * 16)); PT_CK(ctx->w_L.alloc(S * 16));
     PT_CK(ctx->w_rng.alloc(S * 16)); PT_CK(ctx->w_hit.alloc(S * 16)); PT_CK(ctx->w_active.alloc(S * 4)); PT_CK(ctx->w_next.alloc(S * 4));
     PT_CK(ctx->w_sorted.alloc(S * 4)); PT_CK(ctx->w_sh_o.alloc(S * 16)); PT_CK(ctx->w_sh_d.alloc(S * 16)); PT_CK(ctx->w_sh_c.alloc(S * 16));
     if (ctx->attr_enabled) PT_CK(ctx->w_hit_uv.alloc(S * 8)); else ctx->w_hit_uv.release();
-    PT_CK(ctx->w_ctr.alloc(sizeof(PtWaveCounters))); PT_CK(ctx->w_keyhist.alloc((PT_KEY_BUCKETS + 1) * 4));
-    PT_CK(cudaMemsetAsync(ctx->w_ctr.p, 0, sizeof(PtWaveCounters), ctx->stream));
+    PT_CK(ctx->w_ctr.alloc(2 * sizeof(PtWaveCounters))); PT_CK(ctx->w_keyhist.alloc(2 * (PT_KEY_BUCKETS + 1) * 4));
+    PT_CK(cudaMemsetAsync(ctx->w_ctr.p, 0, 2 * sizeof(PtWaveCounters), ctx->stream));
     if (!ctx->d_accum.p) {
         PT_CK(ctx->d_accum.alloc((size_t)W * H * 16));
         PT_CK(cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)W * H * 16, ctx->stream));
@@ -517,22 +539,28 @@ int32_t setup_wave(Ctx* ctx) {
 
 template <bool TWO>
 int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
-    PtWave w;
-    w.ray_o = ctx->w_ray_o.as<float4>(); w.ray_d = ctx->w_ray_d.as<float4>(); w.beta = ctx->w_beta.as<float4>(); w.L = ctx->w_L.as<float4>();
-    w.rng = ctx->w_rng.as<uint4>(); w.hit = ctx->w_hit.as<float4>(); w.active = ctx->w_active.as<uint32_t>(); w.next = ctx->w_next.as<uint32_t>();
-    w.sorted = ctx->w_sorted.as<uint32_t>(); w.sh_o = ctx->w_sh_o.as<float4>(); w.sh_d = ctx->w_sh_d.as<float4>(); w.sh_c = ctx->w_sh_c.as<float4>();
-    w.slot_pixel = ctx->part_count > 1 ? ctx->w_slot_pixel.as<uint32_t>() : nullptr;
-    w.ctr = ctx->w_ctr.as<PtWaveCounters>(); w.key_hist = ctx->w_keyhist.as<uint32_t>(); w.num_slots = ctx->num_slots; w.num_pixels = ctx->num_slots;
+    const size_t S1 = (size_t)ctx->num_slots * ctx->wave_samples;       // slots of one copy of the wavefront state
+    PtWave wset[2];
+    for (int k = 0; k < ctx->wave_sets; ++k) {
+        PtWave& w = wset[k];
+        const size_t o = (size_t)k * S1;
+        w.ray_o = ctx->w_ray_o.as<float4>() + o; w.ray_d = ctx->w_ray_d.as<float4>() + o; w.beta = ctx->w_beta.as<float4>() + o; w.L = ctx->w_L.as<float4>() + o;
+        w.rng = ctx->w_rng.as<uint4>() + o; w.hit = ctx->w_hit.as<float4>() + o; w.active = ctx->w_active.as<uint32_t>() + o; w.next = ctx->w_next.as<uint32_t>() + o;
+        w.sorted = ctx->w_sorted.as<uint32_t>() + o; w.sh_o = ctx->w_sh_o.as<float4>() + o; w.sh_d = ctx->w_sh_d.as<float4>() + o; w.sh_c = ctx->w_sh_c.as<float4>() + o;
+        w.slot_pixel = ctx->part_count > 1 ? ctx->w_slot_pixel.as<uint32_t>() : nullptr;
+        w.ctr = ctx->w_ctr.as<PtWaveCounters>() + k; w.key_hist = ctx->w_keyhist.as<uint32_t>() + (size_t)k * (PT_KEY_BUCKETS + 1);
+        w.num_slots = ctx->num_slots; w.num_pixels = ctx->num_slots;
+        w.hit_uv = ctx->attr_enabled ? ctx->w_hit_uv.as<float2>() + o : nullptr;
+    }
     PtShadeScene ss;
     ss.sv = ctx->view; ss.mats = ctx->d_mats.as<PtMaterial>(); ss.num_mats = (uint32_t)ctx->mats.size();
     ss.mesh_attr = ctx->attr_enabled ? ctx->d_mesh_attr.as<PtMeshAttr>() : nullptr; ss.textures = ctx->d_textures.as<PtTexture>(); ss.mat_tex = ctx->d_mat_tex.as<uint32_t>();
-    w.hit_uv = ctx->attr_enabled ? ctx->w_hit_uv.as<float2>() : nullptr;
     ss.sc.lights = ctx->d_lights.as<PtLight>(); ss.sc.num_lights = ctx->num_lights; ss.sc.light_area = ctx->light_area; ss.sc.ray_eps = ctx->ray_eps;
     ss.sc.flags = ctx->cfg.flags; ss.sc.seed = ctx->cfg.seed; ss.sc.max_bounces = max_bounces;
     ss.sc.bg[0] = ctx->cfg.background[0]; ss.sc.bg[1] = ctx->cfg.background[1]; ss.sc.bg[2] = ctx->cfg.background[2];
     const bool sort = (ctx->cfg.flags & FOUNDATION_PT_FLAG_MATERIAL_SORT) && !(ctx->cfg.flags & FOUNDATION_PT_FLAG_NO_MATERIAL_SORT);
     uint32_t* status = ctx->d_status.as<uint32_t>();
-    // optional per-stage timing: one event per stage boundary, evaluated in foundation_pt_wait
+    // optional per-stage timing: one event per stage boundary, evaluated in foundation_pt_wait (single wave set, see setup_wave)
     const bool timing = (ctx->cfg.flags & FOUNDATION_PT_FLAG_STAGE_TIMING) != 0;
     ctx->stage_marks.clear();
     auto mark = [&](int stage) {
@@ -543,40 +571,53 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
         ctx->stage_marks.push_back(stage);
     };
     mark(-1);
-    for (uint32_t smp = s0; smp < s0 + ns;) {
+    // Waves alternate between the two streams / state copies when the call has more than one wave.  What orders them: (1) a stream runs its own waves in order, so a state
+    // copy is never reused early; (2) the accumulation of wave i waits for the accumulation of wave i - 1 (event), so every pixel still adds its samples in ascending sample
+    // order — the frame stays bit-identical to the one-wave-at-a-time render; (3) the second stream forks from and joins the context's stream around the call.
+    const uint32_t num_waves = (ns + ctx->wave_samples - 1) / ctx->wave_samples;
+    const bool dual = ctx->wave_sets == 2 && num_waves > 1 && !timing;
+    if (dual) { PT_CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); PT_CK(cudaStreamWaitEvent(ctx->stream_b, ctx->ev_fork, 0)); }
+    uint32_t wave = 0;
+    for (uint32_t smp = s0; smp < s0 + ns; ++wave) {
+        const int k = dual ? (int)(wave & 1u) : 0;
+        cudaStream_t st = k ? ctx->stream_b : ctx->stream;
+        PtWave& w = wset[k];
         const uint32_t batch = (s0 + ns - smp) < ctx->wave_samples ? (s0 + ns - smp) : ctx->wave_samples;
         const uint32_t S = ctx->num_slots * batch;
         w.num_slots = S;
         const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8), gtrace = grid_for(ctx, S, 128, trace_blocks(ctx));
         PtFrame f; f.cam = ctx->cam; f.seed = ctx->cfg.seed; f.width = ctx->cfg.width; f.height = ctx->cfg.height; f.sample = smp; f.flags = ctx->cfg.flags;
         smp += batch;
-        w.active = ctx->w_active.as<uint32_t>(); w.next = ctx->w_next.as<uint32_t>();
-        PT_LAUNCH(ctx, k_raygen, g256, 256, w, f);
+        w.active = ctx->w_active.as<uint32_t>() + (size_t)k * S1; w.next = ctx->w_next.as<uint32_t>() + (size_t)k * S1;
+        PT_LAUNCH_ON(ctx, st, k_raygen, g256, 256, w, f);
         mark(0);
         for (uint32_t b = 0; b <= max_bounces; ++b) {
-            if (sort) PT_LAUNCH(ctx, k_key_clear, 2, 1024, w.key_hist);
-            if (w.hit_uv) PT_LAUNCH(ctx, (k_extend<TWO, true>), gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
-            else PT_LAUNCH(ctx, (k_extend<TWO, false>), gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
+            if (sort) PT_LAUNCH_ON(ctx, st, k_key_clear, 2, 1024, w.key_hist);
+            if (w.hit_uv) PT_LAUNCH_ON(ctx, st, (k_extend<TWO, true>), gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
+            else PT_LAUNCH_ON(ctx, st, (k_extend<TWO, false>), gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
             mark(1);
             const uint32_t* list = w.active;
             if (sort) {
-                PT_LAUNCH(ctx, k_key_hist, g256, 256, w);
-                PT_LAUNCH(ctx, k_key_scan, 1, 1024, w.key_hist);
-                PT_LAUNCH(ctx, k_key_scatter, g256, 256, w);
+                PT_LAUNCH_ON(ctx, st, k_key_hist, g256, 256, w);
+                PT_LAUNCH_ON(ctx, st, k_key_scan, 1, 1024, w.key_hist);
+                PT_LAUNCH_ON(ctx, st, k_key_scatter, g256, 256, w);
                 list = w.sorted;
                 mark(4);
             }
-            PT_LAUNCH(ctx, k_shade<TWO>, g128, 128, ss, w, list);
+            PT_LAUNCH_ON(ctx, st, k_shade<TWO>, g128, 128, ss, w, list);
             mark(2);
-            PT_LAUNCH(ctx, k_connect<TWO>, gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
-            PT_LAUNCH(ctx, k_bounce_end, 1, 32, w);
+            PT_LAUNCH_ON(ctx, st, k_connect<TWO>, gtrace, 128, ctx->view, w, status, ctx->fetch_thresh);
+            PT_LAUNCH_ON(ctx, st, k_bounce_end, 1, 32, w);
             mark(3);
             std::swap(w.active, w.next);
         }
-        PT_LAUNCH(ctx, k_accumulate, grid_for(ctx, ctx->num_slots, 256, 8), 256, w, ctx->d_accum.as<float4>(),
-                  (ctx->comm_count > 1 && (ctx->comm_flags & FOUNDATION_PT_COMM_DIRECT) && ctx->comm_rank != 0) ? ctx->remote_accum : nullptr);
+        if (dual && wave > 0) PT_CK(cudaStreamWaitEvent(st, ctx->ev_acc[(wave - 1u) & 1u], 0));
+        PT_LAUNCH_ON(ctx, st, k_accumulate, grid_for(ctx, ctx->num_slots, 256, 8), 256, w, ctx->d_accum.as<float4>(),
+                     (ctx->comm_count > 1 && (ctx->comm_flags & FOUNDATION_PT_COMM_DIRECT) && ctx->comm_rank != 0) ? ctx->remote_accum : nullptr);
+        if (dual) PT_CK(cudaEventRecord(ctx->ev_acc[wave & 1u], st));
         mark(5);
     }
+    if (dual) { PT_CK(cudaEventRecord(ctx->ev_join, ctx->stream_b)); PT_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
     PT_CK(cudaGetLastError());
     return 0;
 }
@@ -796,12 +837,14 @@ int32_t foundation_pt_destroy(foundation_pt_context* ctx) {
     comm_release(ctx);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
+    if (ctx->stream_b) cudaStreamSynchronize(ctx->stream_b);
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_acc[0], ctx->ev_acc[1]}) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2); if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
-    cudaStream_t s1 = ctx->stream, s2 = ctx->stream2, s3 = ctx->stream3;
+    cudaStream_t s1 = ctx->stream, s2 = ctx->stream2, s3 = ctx->stream3, s4 = ctx->stream_b;
     delete ctx;   // frees device buffers
-    if (s1) cudaStreamDestroy(s1); if (s2) cudaStreamDestroy(s2); if (s3) cudaStreamDestroy(s3);
+    if (s1) cudaStreamDestroy(s1); if (s2) cudaStreamDestroy(s2); if (s3) cudaStreamDestroy(s3); if (s4) cudaStreamDestroy(s4);
     return FOUNDATION_PT_OK;
 }
 
@@ -1193,7 +1236,7 @@ int32_t foundation_pt_render_async(foundation_pt_context* ctx, uint32_t sample_b
             if (ctx->num_slots) PT_LAUNCH(ctx, k_clear_owned, grid_for(ctx, ctx->num_slots, 256, 8), 256, ctx->d_accum.as<float4>(), ctx->w_slot_pixel.as<uint32_t>(), ctx->num_slots);
         } else PT_CK(cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)ctx->cfg.width * ctx->cfg.height * 16, ctx->stream));
     }
-    PT_CK(cudaMemsetAsync(ctx->w_ctr.p, 0, sizeof(PtWaveCounters), ctx->stream));
+    PT_CK(cudaMemsetAsync(ctx->w_ctr.p, 0, 2 * sizeof(PtWaveCounters), ctx->stream));
     if (ctx->num_slots) {
         rc = ctx->two_level ? render_impl<true>(ctx, sample_begin, sample_count, max_bounces) : render_impl<false>(ctx, sample_begin, sample_count, max_bounces);
         if (rc) return rc;
@@ -1213,9 +1256,9 @@ int32_t foundation_pt_wait(foundation_pt_context* ctx) {
     PT_CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats.last_ms = ms; ctx->stats.kernel_launches = ctx->call_launches; ctx->stats.total_launches = ctx->total_launches;
-    PtWaveCounters c;
-    PT_CK(cudaMemcpy(&c, ctx->w_ctr.p, sizeof c, cudaMemcpyDeviceToHost));
-    ctx->stats.rays_extend = c.total_extend; ctx->stats.rays_shadow = c.total_shadow;
+    PtWaveCounters c[2];
+    PT_CK(cudaMemcpy(c, ctx->w_ctr.p, sizeof c, cudaMemcpyDeviceToHost));
+    ctx->stats.rays_extend = c[0].total_extend + c[1].total_extend; ctx->stats.rays_shadow = c[0].total_shadow + c[1].total_shadow;
     for (float& v : ctx->stats.stage_ms) v = 0.0f;
     for (size_t i = 1; i < ctx->stage_marks.size(); ++i) {
         float dt = 0.0f;

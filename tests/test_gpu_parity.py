@@ -92,6 +92,31 @@ def test_image_matches_oracle(pair, flags):
     tr.close()
 
 
+@pytest.mark.parametrize("wave_samples", [1, 2])
+def test_two_waves_in_flight_keep_the_frame_bit_identical(pair, monkeypatch, wave_samples):
+    """A render of several waves alternates them between two streams / two copies of the wavefront state (the tails of one wave's traversal kernels overlap the other
+    wave's kernels); the accumulations stay chained in sample order, so the frame equals the one-wave-at-a-time frame and the oracle's bit for bit, and the ray counters add up."""
+    name, sc, _, orc = pair
+    spp, bounces = 5, 4
+    frames, rays = [], []
+    for dual in ("1", "0"):
+        monkeypatch.setenv("FOUNDATION_PT_DUAL_WAVE", dual)
+        monkeypatch.setenv("FOUNDATION_PT_WAVE_SAMPLES", str(wave_samples))      # 5 or 3 waves (the last one short) instead of one
+        tr = pt.PathTracer(sc.width, sc.height, seed=11, background=sc.background)
+        tr.load(sc)
+        tr.render(0, spp, bounces)
+        st = tr.stats()
+        frames.append(tr.read_accum()); rays.append((st.rays_extend, st.rays_shadow))
+        tr.render(0, 2, bounces); tr.render(2, spp - 2, bounces)                  # progressive continuation across calls, again several waves per call
+        frames.append(tr.read_accum())
+        tr.close()
+    rc = np.zeros(2, np.uint64)
+    o = orc.render(sc.width, sc.height, 11, 0, spp, bounces, background=sc.background, ray_counts=rc)
+    for f in frames:
+        assert f.tobytes() == o.tobytes(), f"{name}: frame differs from the oracle's"
+    assert rays[0] == rays[1] and rays[0][0] > 0
+
+
 def test_tile_partition_is_bit_identical(pair):
     """§8e: interleaved tiles -> the union of the ranks' images equals the single-GPU image exactly."""
     name, sc, _, orc = pair
