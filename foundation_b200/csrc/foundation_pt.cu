@@ -311,8 +311,8 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
         PT_CK(cudaMemsetAsync(up_count.p, 0, 4, ctx->stream));
         int& refit_blocks = ctx->refit_blocks;     // resident blocks per SM (shared-memory bound), per context / device: the grid is exactly one wave, tiles are strided over it
 #if PT_AGGLOMERATIVE
-        if (!refit_blocks && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&refit_blocks, k_refit_agg, PT_REFIT_TILE, 0) != cudaSuccess || refit_blocks < 1)) { cudaGetLastError(); refit_blocks = 4; }
-        PT_LAUNCH(ctx, k_refit_agg, grid_for(ctx, n, PT_REFIT_TILE, (uint32_t)refit_blocks), PT_REFIT_TILE, b, keys.as<uint64_t>(), d_prim_box, vals.as<uint32_t>(),
+        if (!refit_blocks && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&refit_blocks, k_refit_agg, PT_REFIT_THREADS, 0) != cudaSuccess || refit_blocks < 1)) { cudaGetLastError(); refit_blocks = 4; }
+        PT_LAUNCH(ctx, k_refit_agg, grid_for(ctx, n, PT_REFIT_TILE, (uint32_t)refit_blocks), PT_REFIT_THREADS, b, keys.as<uint64_t>(), d_prim_box, vals.as<uint32_t>(),
                   up_list.as<uint32_t>(), up_count.as<uint32_t>(), root_ref.as<uint32_t>(), max_leaf);
         if (n > 1) PT_LAUNCH(ctx, k_refit_agg_up, grid_for(ctx, n / 16 + 1, 128, 8), 128, b, keys.as<uint64_t>(), up_list.as<uint32_t>(), up_count.as<uint32_t>(),
                              flags.as<uint32_t>(), root_ref.as<uint32_t>(), max_leaf);

@@ -556,6 +556,9 @@ __device__ __forceinline__ PtBox pt_ldcg_box(const PtBox* p) {
 #ifndef PT_REFIT_TILE
 #define PT_REFIT_TILE 256
 #endif
+#ifndef PT_REFIT_THREADS
+#define PT_REFIT_THREADS 128     // threads of a k_refit_agg block (a tile's rounds hold at most PT_REFIT_TILE / 2 nodes)
+#endif
 __device__ __forceinline__ PtBox pt_lds_box(const PtBox* p) {   // volatile: written by another thread of the block in an earlier round
     const volatile float* f = reinterpret_cast<const volatile float*>(p);
     PtBox b; b.lox = f[0]; b.loy = f[1]; b.loz = f[2]; b.hix = f[3]; b.hiy = f[4]; b.hiz = f[5];
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(128) k_refit_up(PtBvh2 b, const uint32_t* up_l
 // left child [l, r] is local iff the right sibling, which starts at r+1 and ends before the first key that does NOT share more than
 // delta(r, r+1) bits with key r+1, ends inside the tile: one more delta against the key just past the tile (mirrored for right children).
 // Both children evaluate the same predicate, so they meet either in shared memory or through the global protocol, never one in each.
-__global__ void __launch_bounds__(PT_REFIT_TILE) k_refit_agg(PtBvh2 b, const uint64_t* keys, const PtBox* prim_box, const uint32_t* order, uint32_t* up_list,
+__global__ void __launch_bounds__(PT_REFIT_THREADS) k_refit_agg(PtBvh2 b, const uint64_t* keys, const PtBox* prim_box, const uint32_t* order, uint32_t* up_list,
                                                             uint32_t* up_count, uint32_t* root_out, uint32_t max_leaf) {
     constexpr uint32_t T = PT_REFIT_TILE;
     __shared__ PtBox s_box[2 * T];
@@ -735,17 +738,21 @@ __global__ void __launch_bounds__(PT_REFIT_TILE) k_refit_agg(PtBvh2 b, const uin
     if (n == 1) { if (pt_gtid() == 0) b.box[0] = prim_box[order[0]]; return; }
     for (uint32_t tile_lo = blockIdx.x * T; tile_lo < n; tile_lo += gridDim.x * T) {
         const uint32_t tile_hi = min(n, tile_lo + T) - 1u;
-        const uint32_t j = tile_lo + tid;
         const uint32_t koff = tile_lo - 1u;              // s_key[i - koff]; position tile_lo - 1 only exists when tile_lo > 0 (never read otherwise)
-        if (j < n) {
-            const PtBox lb = prim_box[order[j]];
-            s_box[T + tid] = lb;
-            b.box[n - 1 + j] = lb;
-            s_key[tid + 1] = keys[j];
+        // PT_REFIT_THREADS threads serve a tile of T leaves: a round never holds more than T / 2 nodes, so T / 2 threads are enough for the rounds and
+        // half as many warps wait at every round barrier; the per-leaf phases (load, write back) take T / PT_REFIT_THREADS passes
+        for (uint32_t t = tid; t < T; t += PT_REFIT_THREADS) {
+            const uint32_t j = tile_lo + t;
+            if (j < n) {
+                const PtBox lb = prim_box[order[j]];
+                s_box[T + t] = lb;
+                b.box[n - 1 + j] = lb;
+                s_key[t + 1] = keys[j];
+            }
+            s_flag[t] = 0;
         }
         if (tid == 0 && tile_lo > 0) s_key[0] = keys[tile_lo - 1];
         if (tid == 0 && tile_hi + 1 < n) s_key[tile_hi + 2 - tile_lo] = keys[tile_hi + 1];
-        s_flag[tid] = 0;
         if (tid == 0) { s_qn[0] = 0; s_qn[1] = 0; s_qn[2] = 0; s_upn = 0; }
         __syncthreads();
         // subtree `ref` over [l, r] (inside the tile) is finished: find its parent, hand it over
@@ -759,14 +766,14 @@ __global__ void __launch_bounds__(PT_REFIT_TILE) k_refit_agg(PtBvh2 b, const uin
             __threadfence_block();
             if (atomicAdd(&s_flag[lp], 1u) == 1u) s_q[q][atomicAdd(&s_qn[q], 1u)] = jn.p;
         };
-        if (j < n) deliver(n - 1 + j, j, j, 0u);
+        for (uint32_t t = tid; t < T; t += PT_REFIT_THREADS) { const uint32_t j = tile_lo + t; if (j < n) deliver(n - 1 + j, j, j, 0u); }
         __syncthreads();
         for (uint32_t cur = 0;; cur = cur == 2u ? 0u : cur + 1u) {
             const uint32_t cnt = s_qn[cur], nxt = cur == 2u ? 0u : cur + 1u;
             if (cnt == 0) break;
             if (tid == 0) s_qn[nxt == 2u ? 0u : nxt + 1u] = 0;
-            if (tid < cnt) {
-                const uint32_t p = s_q[cur][tid], lp = p - tile_lo;
+            for (uint32_t qi = tid; qi < cnt; qi += PT_REFIT_THREADS) {
+                const uint32_t p = s_q[cur][qi], lp = p - tile_lo;
                 const uint32_t L = *const_cast<volatile uint32_t*>(&s_left[lp]), R = *const_cast<volatile uint32_t*>(&s_right[lp]);
                 const uint32_t f = *const_cast<volatile uint32_t*>(&s_first[lp]), la = *const_cast<volatile uint32_t*>(&s_last[lp]);
                 float cl[7], cr[7], mc[7];
@@ -802,17 +809,20 @@ __global__ void __launch_bounds__(PT_REFIT_TILE) k_refit_agg(PtBvh2 b, const uin
             __syncthreads();
         }
         // write back the nodes finished in this tile: boxes, costs, plan AND their topology (the collapse reads left / right / first / last)
-        if (j < n - 1 && s_flag[tid] == 2u) {
-            b.box[j] = s_box[tid];
-            float4* dst = reinterpret_cast<float4*>(b.cost + 8 * (size_t)j);
-            dst[0] = s_cost[tid][0]; dst[1] = s_cost[tid][1];
-            b.plan[j] = s_plan[tid];
-            b.left[j] = s_left[tid]; b.right[j] = s_right[tid]; b.first[j] = s_first[tid]; b.last[j] = s_last[tid];
+        for (uint32_t t = tid; t < T; t += PT_REFIT_THREADS) {
+            const uint32_t j = tile_lo + t;
+            if (j < n - 1 && s_flag[t] == 2u) {
+                b.box[j] = s_box[t];
+                float4* dst = reinterpret_cast<float4*>(b.cost + 8 * (size_t)j);
+                dst[0] = s_cost[t][0]; dst[1] = s_cost[t][1];
+                b.plan[j] = s_plan[t];
+                b.left[j] = s_left[t]; b.right[j] = s_right[t]; b.first[j] = s_first[t]; b.last[j] = s_last[t];
+            }
         }
         __syncthreads();
         if (tid == 0) s_qn[0] = atomicAdd(up_count, s_upn);
         __syncthreads();
-        if (tid < s_upn) up_list[s_qn[0] + tid] = s_up[tid];
+        for (uint32_t t = tid; t < s_upn; t += PT_REFIT_THREADS) up_list[s_qn[0] + t] = s_up[t];
         __syncthreads();
     }
 }
