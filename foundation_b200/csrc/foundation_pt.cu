@@ -574,7 +574,10 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
     // Waves alternate between the two streams / state copies when the call has more than one wave.  What orders them: (1) a stream runs its own waves in order, so a state
     // copy is never reused early; (2) the accumulation of wave i waits for the accumulation of wave i - 1 (event), so every pixel still adds its samples in ascending sample
     // order — the frame stays bit-identical to the one-wave-at-a-time render; (3) the second stream forks from and joins the context's stream around the call.
-    const uint32_t num_waves = (ns + ctx->wave_samples - 1) / ctx->wave_samples;
+    // a call that fits one wave (a rank of a multi-GPU frame owns few pixels, so 64 samples of them are one wave) is cut in two halves when both are still large
+    uint32_t wave_samples = ctx->wave_samples;
+    if (ctx->wave_sets == 2 && !timing && ns >= 2 && ns <= wave_samples && (uint64_t)ctx->num_slots * ns >= (1ull << 23)) wave_samples = (ns + 1) / 2;
+    const uint32_t num_waves = (ns + wave_samples - 1) / wave_samples;
     const bool dual = ctx->wave_sets == 2 && num_waves > 1 && !timing;
     if (dual) { PT_CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); PT_CK(cudaStreamWaitEvent(ctx->stream_b, ctx->ev_fork, 0)); }
     uint32_t wave = 0;
@@ -582,7 +585,7 @@ int32_t render_impl(Ctx* ctx, uint32_t s0, uint32_t ns, uint32_t max_bounces) {
         const int k = dual ? (int)(wave & 1u) : 0;
         cudaStream_t st = k ? ctx->stream_b : ctx->stream;
         PtWave& w = wset[k];
-        const uint32_t batch = (s0 + ns - smp) < ctx->wave_samples ? (s0 + ns - smp) : ctx->wave_samples;
+        const uint32_t batch = (s0 + ns - smp) < wave_samples ? (s0 + ns - smp) : wave_samples;
         const uint32_t S = ctx->num_slots * batch;
         w.num_slots = S;
         const uint32_t g256 = grid_for(ctx, S, 256, 8), g128 = grid_for(ctx, S, 128, 8), gtrace = grid_for(ctx, S, 128, trace_blocks(ctx));

@@ -85,3 +85,29 @@ def test_config5_4k_eight_tile_partitions_sum_to_the_whole_frame(gpu):
     assert np.all(total[..., 3] == 2.0)
     assert np.array_equal(total, whole), f"4K: {int((total != whole).any(-1).sum())} pixels differ between the 8-way partition and the whole frame"
     tr.close()
+
+
+def test_fullsize_two_waves_in_flight_are_bit_identical_to_one_wave_at_a_time(gpu, monkeypatch):
+    """The wave logic at sizes the miniatures cannot reach: (a) a 1080p call that fits ONE wave but is large enough to be cut into two halves on two streams (5 samples =
+    10.4 M slots), (b) a call of several full waves plus a short one (37 samples at 16 per wave), (c) one rank's share of an 8-GPU frame (64 samples of 1/8 of the pixels —
+    one wave by size, two by the split rule).  Each must equal, bit for bit, the same samples rendered one wave at a time (FOUNDATION_PT_DUAL_WAVE=0), ray counters included."""
+    sc = scenes.sphere_field()
+    frames, rays = {}, {}
+    for dual in ("1", "0"):
+        monkeypatch.setenv("FOUNDATION_PT_DUAL_WAVE", dual)
+        tr = pt.PathTracer(sc.width, sc.height, seed=9, background=sc.background)
+        tr.load(sc)
+        out, cnt = [], []
+        for s0, ns in ((0, 5), (0, 37)):
+            tr.render(s0, ns, 8)
+            st = tr.stats()
+            out.append(tr.read_accum().copy()); cnt.append((st.rays_extend, st.rays_shadow))
+        tr.partition_set(0, 8, 32)
+        tr.render(0, 64, 8)
+        st = tr.stats()
+        out.append(tr.read_accum().copy()); cnt.append((st.rays_extend, st.rays_shadow))
+        tr.close()
+        frames[dual], rays[dual] = out, cnt
+    for k, what in enumerate(("5 samples (one wave cut in two)", "37 samples (three waves)", "rank 0 of 8, 64 samples")):
+        assert frames["1"][k].tobytes() == frames["0"][k].tobytes(), what
+        assert rays["1"][k] == rays["0"][k] and rays["1"][k][0] > 0, what
