@@ -227,7 +227,7 @@ inline uint32_t trace_blocks(const Ctx* ctx) {   // persistent grid of the trave
 // ------------------------------------------------------------------------------------------------
 // device exclusive scan (in place allowed); total written to d_total (device uint32) if non-null
 // ------------------------------------------------------------------------------------------------
-int32_t scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf& chunk_sums, uint32_t* d_total) {
+[[maybe_unused]] int32_t scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n, DevBuf& chunk_sums, uint32_t* d_total) {   // used by the non-default sort / collapse paths
     uint32_t chunks = (n + PT_SCAN_CHUNK - 1) / PT_SCAN_CHUNK;
     if (chunks == 0) chunks = 1;
     const size_t state_bytes = ((size_t)chunks + 1) * 8;          // one status word per tile + the ticket counter
@@ -329,7 +329,10 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
     PT_CK(out->leaf_seq.alloc((size_t)n * 4));
     PT_CK(totals.alloc(16));
     PT_CK(cudaMemcpyAsync(refs_a.p, root_ref.p, 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    uint32_t m = 1, level_start = 0, prim_total = 0;
+#if !PT_COLLAPSE_PERSISTENT
+    uint32_t m = 1;
+#endif
+    uint32_t level_start = 0, prim_total = 0;
     {   // top of the tree: all levels of at most PT_TOP_NODES wide nodes in one single-block launch
         PT_LAUNCH(ctx, k_collapse_top, 1, PT_TOP_NODES, b, refs_a.as<uint32_t>(), refs_b.as<uint32_t>(), max_leaf, d_bp, nodes_tmp.as<PtNode8>(), out->leaf_seq.as<uint32_t>(),
                   totals.as<uint32_t>());
@@ -370,7 +373,7 @@ int32_t build_bvh8(Ctx* ctx, uint32_t n, const PtBox* d_prim_box, DevBuf& keys, 
         PT_CK(cudaMemcpyAsync(st, totals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
         PT_CK(cudaStreamSynchronize(ctx->stream));
         if (st[3] || st[0]) return ctx->fail(FOUNDATION_PT_ERR_STATE, "BVH8 collapse exceeded node capacity");
-        level_start = st[1]; prim_total = st[2]; m = 0;
+        level_start = st[1]; prim_total = st[2];
     }
 #else
     size_t cap = 0;
