@@ -525,11 +525,23 @@ int32_t setup_wave(Ctx* ctx) {
             cudaEventCreateWithFlags(&ctx->ev_acc[1], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ctx->wave_sets = 1; }
     }
     const size_t S1 = (size_t)(ctx->num_slots ? ctx->num_slots : 1) * ctx->wave_samples;
-    const size_t S = S1 * (size_t)ctx->wave_sets;
-    PT_CK(ctx->w_ray_o.alloc(S * 16)); PT_CK(ctx->w_ray_d.alloc(S * 16)); PT_CK(ctx->w_beta.alloc(S * 16)); PT_CK(ctx->w_L.alloc(S * 16));
-    PT_CK(ctx->w_rng.alloc(S * 16)); PT_CK(ctx->w_hit.alloc(S * 16)); PT_CK(ctx->w_active.alloc(S * 4)); PT_CK(ctx->w_next.alloc(S * 4));
-    PT_CK(ctx->w_sorted.alloc(S * 4)); PT_CK(ctx->w_sh_o.alloc(S * 16)); PT_CK(ctx->w_sh_d.alloc(S * 16)); PT_CK(ctx->w_sh_c.alloc(S * 16));
-    if (ctx->attr_enabled) PT_CK(ctx->w_hit_uv.alloc(S * 8)); else ctx->w_hit_uv.release();
+    auto alloc_state = [&](size_t S) -> cudaError_t {
+        struct { DevBuf* b; size_t bytes; } bufs[] = {{&ctx->w_ray_o, 16}, {&ctx->w_ray_d, 16}, {&ctx->w_beta, 16}, {&ctx->w_L, 16}, {&ctx->w_rng, 16}, {&ctx->w_hit, 16},
+                                                      {&ctx->w_active, 4}, {&ctx->w_next, 4}, {&ctx->w_sorted, 4}, {&ctx->w_sh_o, 16}, {&ctx->w_sh_d, 16}, {&ctx->w_sh_c, 16}};
+        for (auto& x : bufs) { cudaError_t e = x.b->alloc(S * x.bytes); if (e != cudaSuccess) return e; }
+        if (ctx->attr_enabled) return ctx->w_hit_uv.alloc(S * 8);
+        ctx->w_hit_uv.release();
+        return cudaSuccess;
+    };
+    cudaError_t ea = alloc_state(S1 * (size_t)ctx->wave_sets);
+    if (ea == cudaErrorMemoryAllocation && ctx->wave_sets == 2) {      // no room for the second copy: one wave at a time
+        cudaGetLastError();
+        for (DevBuf* b : {&ctx->w_ray_o, &ctx->w_ray_d, &ctx->w_beta, &ctx->w_L, &ctx->w_rng, &ctx->w_hit, &ctx->w_active, &ctx->w_next, &ctx->w_sorted, &ctx->w_sh_o, &ctx->w_sh_d,
+                          &ctx->w_sh_c, &ctx->w_hit_uv}) b->release();
+        ctx->wave_sets = 1;
+        ea = alloc_state(S1);
+    }
+    PT_CK(ea);
     PT_CK(ctx->w_ctr.alloc(2 * sizeof(PtWaveCounters))); PT_CK(ctx->w_keyhist.alloc(2 * (PT_KEY_BUCKETS + 1) * 4));
     PT_CK(cudaMemsetAsync(ctx->w_ctr.p, 0, 2 * sizeof(PtWaveCounters), ctx->stream));
     if (!ctx->d_accum.p) {
