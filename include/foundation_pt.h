@@ -237,7 +237,10 @@ FOUNDATION_PT_API const char* foundation_pt_group_last_error(const foundation_pt
 
 /* ---- render (reference slot: Renderer::Record's pass body, Renderer.cpp:332-351, driven by Draw :367-401) ----
  * Adds samples [sample_begin, sample_begin + sample_count) of every owned pixel to the accumulation buffer.
- * sample_begin == 0 clears the buffer first. */
+ * sample_begin == 0 clears the buffer first.
+ * Memory: the first render of a context allocates the wavefront state — up to 32 M path slots (about 5.2 GB) per copy, two copies so that two waves of a
+ * call can be in flight (FOUNDATION_PT_DUAL_WAVE=0 or FOUNDATION_PT_FLAG_STAGE_TIMING: one copy; one copy is also the fallback when the second does not fit).
+ * The result does not depend on the number of copies or on how a call is cut into waves: every pixel adds its samples in ascending sample order. */
 FOUNDATION_PT_API int32_t foundation_pt_render(foundation_pt_context* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces);
 /* Asynchronous form (SURVEY.md section 8b "an async variant (render_async + wait) is optional"): render_async only enqueues the same work on
  * the context's stream and returns; wait blocks until it has finished, fills the stats and reports a traversal-stack overflow exactly like
