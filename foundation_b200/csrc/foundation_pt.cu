@@ -107,6 +107,9 @@ struct Mesh {
     DevBuf d_nodes, d_tris, d_order;
     uint32_t num_nodes = 0;
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, pad = 0;
+    // emissive triangles of the mesh (ascending), valid for the emissive set of the materials they were extracted with: a commit that only moves instances
+    // or rebuilds a deformed mesh reuses them (one kernel and two host round trips less per mesh and commit)
+    std::vector<uint32_t> em_tris; std::vector<uint8_t> em_for; bool em_valid = false;
     PtMeshRaw raw() const { PtMeshRaw r; r.pos = d_pos.as<uint8_t>(); r.stride = stride; r.idx = d_idx.p; r.idx_fmt = idx_fmt; r.ntris = ntris; r.mat = d_mat.as<uint32_t>(); return r; }
     void host_tri(uint32_t i, float* v9) const {
         uint32_t id[3];
@@ -1126,11 +1129,15 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
     for (size_t k = 0; k < ctx->mats.size(); ++k) { const PtMaterial& mt = ctx->mats[k]; mat_em[k] = (mt.er > 0 || mt.eg > 0 || mt.eb > 0) ? 1 : 0; any_emissive |= mat_em[k] != 0; }
     if (any_emissive) {
         DevBuf d_em, d_cnt;
-        PT_CK(d_em.alloc(mat_em.size())); PT_CK(d_cnt.alloc(16));
-        PT_CK(cudaMemcpyAsync(d_em.p, mat_em.data(), mat_em.size(), cudaMemcpyHostToDevice, ctx->stream));
-        std::vector<std::vector<uint32_t>> em_tris(ctx->meshes.size());
+        bool uploaded = false;
         for (size_t k = 0; k < ctx->meshes.size(); ++k) {
             Mesh& m = ctx->meshes[k];
+            if (m.em_valid && m.em_for == mat_em) continue;              // same mesh (material ids are fixed at mesh_create), same emissive materials
+            if (!uploaded) {
+                PT_CK(d_em.alloc(mat_em.size())); PT_CK(d_cnt.alloc(16));
+                PT_CK(cudaMemcpyAsync(d_em.p, mat_em.data(), mat_em.size(), cudaMemcpyHostToDevice, ctx->stream));
+                uploaded = true;
+            }
             DevBuf d_list; PT_CK(d_list.alloc((size_t)m.ntris * 4));
             PT_CK(cudaMemsetAsync(d_cnt.p, 0, 4, ctx->stream));
             PT_LAUNCH(ctx, k_emissive_list, grid_for(ctx, m.ntris, 256, 8), 256, m.d_mat.as<uint32_t>(), m.ntris, d_em.as<uint8_t>(), (uint32_t)mat_em.size(), d_list.as<uint32_t>(),
@@ -1138,14 +1145,15 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
             uint32_t cnt = 0;
             PT_CK(cudaMemcpyAsync(&cnt, d_cnt.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
             PT_CK(cudaStreamSynchronize(ctx->stream));
-            em_tris[k].resize(cnt);
-            if (cnt) PT_CK(cudaMemcpyAsync(em_tris[k].data(), d_list.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            m.em_tris.resize(cnt);
+            if (cnt) PT_CK(cudaMemcpyAsync(m.em_tris.data(), d_list.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
             PT_CK(cudaStreamSynchronize(ctx->stream));
-            std::sort(em_tris[k].begin(), em_tris[k].end());
+            std::sort(m.em_tris.begin(), m.em_tris.end());
+            m.em_for = mat_em; m.em_valid = true;
         }
         auto add_mesh_lights = [&](size_t mesh_index, const float* o2w) {
             const Mesh& m = ctx->meshes[mesh_index];
-            for (uint32_t t : em_tris[mesh_index]) {
+            for (uint32_t t : m.em_tris) {
                 uint32_t mid = m.h_mat[t];
                 const PtMaterial& mt = ctx->mats[mid < ctx->mats.size() ? mid : 0];
                 float v[9]; m.host_tri(t, v);
@@ -1157,7 +1165,7 @@ int32_t foundation_pt_scene_commit(foundation_pt_context* ctx, foundation_pt_bui
         };
         if (ctx->two_level) {
             for (uint32_t i = 0; i < ctx->num_inst; ++i)
-                if (!em_tris[ctx->insts[i].mesh_id].empty()) add_mesh_lights(ctx->insts[i].mesh_id, ctx->insts[i].transform);
+                if (!ctx->meshes[ctx->insts[i].mesh_id].em_tris.empty()) add_mesh_lights(ctx->insts[i].mesh_id, ctx->insts[i].transform);
         }
         else add_mesh_lights(0, nullptr);
     }

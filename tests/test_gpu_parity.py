@@ -496,3 +496,33 @@ def test_deforming_mesh_rebuilds_its_blas_and_matches_a_fresh_build(gpu):
         with pytest.raises(pt.FoundationPtError):
             tr.mesh_update_positions(0, pos2[:-1])                                        # topology is fixed
         tr.close()
+
+
+def test_changing_the_emissive_materials_refreshes_the_cached_light_lists(gpu):
+    """The emissive triangles of a mesh are extracted once and reused by later commits (moving instances, deformed meshes); the cache is keyed by the emissive
+    set of the materials, so a commit after materials_set with a different emitter must light the scene from the new emitter — image vs the oracle on the edited scene."""
+    import copy
+    sc = scenes.cornell_box(96, 96)
+    tr = pt.PathTracer(sc.width, sc.height, seed=13, background=sc.background)
+    tr.load(sc)
+    tr.render(0, 2, 3)
+    first = tr.read_accum().copy()
+    sc2 = copy.copy(sc)
+    mats = sc.materials.copy()
+    em = mats[:, 4:7].copy()
+    light = int(np.argmax(em.sum(axis=1)))
+    mats[light, 4:7] = 0.0                                  # the ceiling panel goes dark ...
+    mats[1, 4:7] = (6.0, 2.0, 1.0)                          # ... and the red wall glows instead
+    sc2.materials = mats
+    tr.materials_set(mats)
+    tr.scene_commit()
+    tr.render(0, 2, 3)
+    second = tr.read_accum().copy()
+    o = OracleScene(sc2).render(sc.width, sc.height, 13, 0, 2, 3, background=sc.background)
+    assert second.tobytes() == o.tobytes(), "frame after the material edit differs from the oracle's"
+    assert first.tobytes() != second.tobytes()
+    tr.materials_set(sc.materials)                          # and back: the first list is extracted again, not the stale one reused
+    tr.scene_commit()
+    tr.render(0, 2, 3)
+    assert tr.read_accum().tobytes() == first.tobytes()
+    tr.close()
